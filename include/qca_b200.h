@@ -1,0 +1,163 @@
+/*
+ * qca_b200.h -- C ABI of the B200-native time-evolution path of the quantum
+ * cellular automaton ("quantum game of life") simulator.
+ *
+ * Drop-in boundary: every entry point below replaces one piece of the
+ * reference's (BenjaminDecker/quantum-cellular-automaton) Python hot path; the
+ * reference file:line is cited beside each.  Plain pointers and sizes only, no
+ * torch/numpy types.  All functions return QCA_OK (0) or a QCA_ERR_* code; the
+ * message of the last failure on the calling thread is in qca_last_error().
+ *
+ * Conventions (identical to the reference): cell 0 is the MOST significant bit
+ * of the basis-state index (tensor_networks/mps.py:194-208), one time step
+ * applies exp(-i*pi/2*step_size*H) (lautils/lautils.py:45-55), host state
+ * vectors are interleaved complex128 (numpy complex128, re,im,re,im...).
+ *
+ * There is no CPU fallback: every compute entry point needs an sm_100 device
+ * and fails with QCA_ERR_CUDA otherwise.
+ */
+#ifndef QCA_B200_H
+#define QCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCA_OK 0
+#define QCA_ERR_ARG 1         /* bad argument (reference: assert / ValueError) */
+#define QCA_ERR_CUDA 2        /* CUDA runtime failure or no device */
+#define QCA_ERR_NOMEM 3       /* state does not fit in device memory */
+#define QCA_ERR_STATE 4       /* call order (e.g. step before set_state) */
+#define QCA_ERR_UNSUPPORTED 5 /* rule outside the kernel's range (distance > 7, ncells > 40) */
+
+/* parameters/rules.py:1-6 (periodic is always False in the reference, parser.py:182-187) */
+typedef struct qca_rule {
+    int32_t ncells;   /* --num-cells */
+    int32_t distance; /* --distance */
+    int32_t act_lo;   /* --activation-interval LOWER (inclusive) */
+    int32_t act_hi;   /* --activation-interval UPPER (exclusive) */
+} qca_rule_t;
+
+const char* qca_version(void);
+const char* qca_last_error(void);
+/* number of CUDA devices visible, or 0 */
+int32_t qca_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Host-only planning helpers (no GPU needed; used by the CPU test-suite).
+ * ---------------------------------------------------------------------- */
+
+/* Upper bound of the spectral radius of H = sum_i sx_i P_i: the largest number
+ * of simultaneously active cells over all configurations (Gershgorin row sum of
+ * MPO.as_matrix(), mpo.py:221-230), by a transfer-matrix DP over the chain. */
+int32_t qca_spectral_bound(const qca_rule_t* rule, double* bound);
+
+/* Chebyshev/Bessel plan for exp(-i z x), |x| <= 1:  a[k] = (2 - delta_k0) J_k(z),
+ * k = 0..*nterms-1, truncated where the tail sum drops below tol.  a may be
+ * NULL to query *nterms.  Replaces the eigendecomposition in calculate_U
+ * (lautils.py:52-55). */
+int32_t qca_chebyshev_plan(double z, double tol, double* a, int32_t capacity, int32_t* nterms);
+
+/* One tile pass of the matrix-free operator (see DESIGN.md "pass plan"):
+ * a CTA stages the amplitudes whose index bits [0,low_bits) and
+ * [high_start, high_start+high_bits) vary and applies the rule terms whose
+ * flipped qubit is in flip_mask. */
+typedef struct qca_pass {
+    int32_t low_bits;
+    int32_t high_start;
+    int32_t high_bits;
+    int32_t reserved;
+    uint64_t flip_mask;
+} qca_pass_t;
+/* Plan for a local register of local_bits qubits; returns the number of passes
+ * written to passes[0..capacity). */
+int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity, int32_t* npasses);
+
+/* ------------------------------------------------------------------------
+ * Exact evolution engine == algorithms/exact.py:9-27 (class Exact).
+ * ---------------------------------------------------------------------- */
+typedef struct qca_exact* qca_exact_t;
+
+#define QCA_FLAG_FORCE_COMPLEX 1u /* keep both real planes even if the rotated state is real */
+#define QCA_FLAG_PROFILE 2u       /* record a CUDA-event pair around every kernel launch */
+
+/* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U
+ * (dense 2^N x 2^N) the engine keeps only the rule.  world_size/rank shard the
+ * state over the top log2(world_size) qubits (world_size in {1,2,4,8}); with
+ * world_size > 1 the caller must exchange peer handles (below) before stepping.
+ * stream: a cudaStream_t to launch on, or NULL for an engine-owned stream. */
+int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t device,
+                         int32_t world_size, int32_t rank, uint32_t flags, void* stream);
+int32_t qca_exact_destroy(qca_exact_t h);
+
+/* number of amplitudes held by this rank: 2^(ncells - log2(world_size)) */
+uint64_t qca_exact_local_amps(qca_exact_t h);
+
+/* Exact.psi setter (exact.py:22-24): psi is this rank's contiguous slice of
+ * MPS.as_vector() (mps.py:194-208), namps interleaved complex128. */
+int32_t qca_exact_set_state(qca_exact_t h, const double* psi, uint64_t namps);
+/* MPS.from_density_distribution (mps.py:35-52) + as_vector, evaluated on the
+ * device: amplitude of cell i is (sqrt(1-p_i), sqrt(p_i)). */
+int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_t ncells);
+/* Exact.psi getter, vector part (exact.py:19-20). */
+int32_t qca_exact_get_state(qca_exact_t h, double* psi, uint64_t namps);
+
+/* Exact.do_time_step (exact.py:26-27) x nsteps with U = calculate_U(H, step_size)
+ * (lautils.py:45-55): psi <- exp(-i*pi/2*step_size*H)^nsteps psi, device resident. */
+int32_t qca_exact_step(qca_exact_t h, double step_size, int32_t nsteps);
+
+/* MPS.measure (mps.py:100-140) on MPS.from_vector(psi) (mps.py:55-73): per-cell
+ * population <P1>, np.round of it, single-site von-Neumann entropy in bits, and
+ * the bond dimensions min(2^i, 2^(N-i)) of the exact MPS.  Any pointer may be
+ * NULL.  With world_size > 1 the raw partial sums must be all-reduced by the
+ * caller: use qca_exact_measure_partial + qca_measure_finish instead. */
+int32_t qca_exact_measure(qca_exact_t h, double* population, double* d_population,
+                          double* entropy, double* bond_dims);
+/* sums[4*cell + {0,1,2,3}] = sum|psi_0|^2, sum|psi_1|^2, Re w, Im w with
+ * w = sum_{rest} psi[cell=0,rest] conj(psi[cell=1,rest]) over this rank's slice. */
+int32_t qca_exact_measure_partial(qca_exact_t h, double* sums /* 4*ncells */);
+int32_t qca_measure_finish(const double* sums, int32_t ncells, double* population,
+                           double* d_population, double* entropy, double* bond_dims);
+
+/* Test hook: out = MPO.as_matrix() @ in (mpo.py:221-230) without changing the
+ * engine's state; in/out are this rank's slices, interleaved complex128. */
+int32_t qca_exact_apply_h(qca_exact_t h, const double* in, double* out, uint64_t namps);
+
+/* Squared norm of the resident state (this rank's slice). */
+int32_t qca_exact_norm2(qca_exact_t h, double* norm2);
+
+typedef struct qca_exact_stats {
+    double spectral_bound;       /* R used to scale H */
+    int32_t planes;              /* 1: rotated state is real, 2: general complex */
+    int32_t passes_per_apply;    /* tile passes per operator application */
+    int32_t last_terms;          /* Chebyshev terms of the last step */
+    int32_t local_bits;
+    uint64_t kernel_launches;    /* launches of this library's kernels so far */
+    uint64_t pass_launches;      /* ... of which tile-pass kernels */
+    double pass_bytes;           /* algorithmic bytes moved by those pass launches */
+    double profiled_pass_ms;     /* sum of event-timed pass durations (QCA_FLAG_PROFILE) */
+    uint64_t profiled_pass_launches;
+    double device_bytes;         /* bytes of device memory held */
+} qca_exact_stats_t;
+int32_t qca_exact_get_stats(qca_exact_t h, qca_exact_stats_t* out);
+int32_t qca_exact_reset_stats(qca_exact_t h);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  The state is sharded over the top
+ * log2(world_size) qubits; terms that flip a sharded qubit read the partner
+ * rank's vector directly over NVLink (CUDA IPC peer mapping).  The host side
+ * (torch.distributed) only moves these 64-byte handles once at start-up.
+ * ---------------------------------------------------------------------- */
+#define QCA_IPC_HANDLE_BYTES 64
+/* number of device buffers this rank exports */
+int32_t qca_exact_ipc_count(qca_exact_t h);
+int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IPC_HANDLE_BYTES]);
+/* handles: [world_size][count][QCA_IPC_HANDLE_BYTES] gathered from all ranks */
+int32_t qca_exact_ipc_import(qca_exact_t h, const uint8_t* handles, int32_t world_size, int32_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCA_B200_H */

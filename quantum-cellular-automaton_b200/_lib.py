@@ -1,0 +1,239 @@
+"""ctypes binding of ``libqca_b200.so`` (C ABI in ``include/qca_b200.h``).
+
+There is no fallback: if the shared library is missing the import fails with
+build instructions, and every compute call raises ``QcaError`` when no sm_100
+device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path() -> str:
+    return os.path.join(_PKG, "libqca_b200.so")
+
+
+class QcaError(RuntimeError):
+    """A C-ABI call returned a QCA_ERR_* code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"qca_b200 error {code}: {message}")
+        self.code = code
+
+
+QCA_OK, QCA_ERR_ARG, QCA_ERR_CUDA, QCA_ERR_NOMEM, QCA_ERR_STATE, QCA_ERR_UNSUPPORTED = range(6)
+QCA_FLAG_FORCE_COMPLEX = 1
+QCA_FLAG_PROFILE = 2
+QCA_IPC_HANDLE_BYTES = 64
+
+
+class RuleStruct(C.Structure):
+    _fields_ = [("ncells", C.c_int32), ("distance", C.c_int32), ("act_lo", C.c_int32), ("act_hi", C.c_int32)]
+
+
+class PassStruct(C.Structure):
+    _fields_ = [("low_bits", C.c_int32), ("high_start", C.c_int32), ("high_bits", C.c_int32),
+                ("reserved", C.c_int32), ("flip_mask", C.c_uint64)]
+
+
+class ExactStats(C.Structure):
+    _fields_ = [("spectral_bound", C.c_double), ("planes", C.c_int32), ("passes_per_apply", C.c_int32),
+                ("last_terms", C.c_int32), ("local_bits", C.c_int32), ("kernel_launches", C.c_uint64),
+                ("pass_launches", C.c_uint64), ("pass_bytes", C.c_double), ("profiled_pass_ms", C.c_double),
+                ("profiled_pass_launches", C.c_uint64), ("device_bytes", C.c_double)]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+_dp = C.POINTER(C.c_double)
+
+# every symbol include/qca_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "qca_version": (C.c_char_p, []),
+    "qca_last_error": (C.c_char_p, []),
+    "qca_device_count": (C.c_int32, []),
+    "qca_spectral_bound": (C.c_int32, [C.POINTER(RuleStruct), _dp]),
+    "qca_chebyshev_plan": (C.c_int32, [C.c_double, C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
+    "qca_plan_passes": (C.c_int32, [C.c_int32, C.POINTER(PassStruct), C.c_int32, C.POINTER(C.c_int32)]),
+    "qca_exact_create": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(RuleStruct), C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_uint32, C.c_void_p]),
+    "qca_exact_destroy": (C.c_int32, [C.c_void_p]),
+    "qca_exact_local_amps": (C.c_uint64, [C.c_void_p]),
+    "qca_exact_set_state": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "qca_exact_set_product_state": (C.c_int32, [C.c_void_p, _dp, C.c_int32]),
+    "qca_exact_get_state": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "qca_exact_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32]),
+    "qca_exact_measure": (C.c_int32, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "qca_exact_measure_partial": (C.c_int32, [C.c_void_p, _dp]),
+    "qca_measure_finish": (C.c_int32, [_dp, C.c_int32, _dp, _dp, _dp, _dp]),
+    "qca_exact_apply_h": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "qca_exact_norm2": (C.c_int32, [C.c_void_p, _dp]),
+    "qca_exact_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(ExactStats)]),
+    "qca_exact_reset_stats": (C.c_int32, [C.c_void_p]),
+    "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
+    "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+}
+
+
+def _load() -> C.CDLL:
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: the CUDA extension is not built and there is no CPU fallback. "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C quantum-cellular-automaton_b200/csrc` (needs nvcc, targets sm_100a).")
+    dll = C.CDLL(path)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(dll, name)  # AttributeError if the header and the library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return dll
+
+
+lib = _load()
+
+
+def check(code: int) -> None:
+    if code != QCA_OK:
+        raise QcaError(code, lib.qca_last_error().decode("utf-8", "replace"))
+
+
+def as_double_ptr(arr: np.ndarray):
+    assert arr.dtype == np.float64 and arr.flags.c_contiguous
+    return arr.ctypes.data_as(_dp)
+
+
+def rule_struct(rules) -> RuleStruct:
+    iv = rules.activation_interval
+    return RuleStruct(int(rules.ncells), int(rules.distance), int(iv.start), int(iv.stop))
+
+
+# ---------------------------------------------------------------------------
+# Host-only planning helpers
+# ---------------------------------------------------------------------------
+def spectral_bound(rules) -> float:
+    out = C.c_double()
+    rs = rule_struct(rules)
+    check(lib.qca_spectral_bound(C.byref(rs), C.byref(out)))
+    return out.value
+
+
+def chebyshev_plan(z: float, tol: float = 1e-15) -> np.ndarray:
+    n = C.c_int32()
+    check(lib.qca_chebyshev_plan(z, tol, None, 0, C.byref(n)))
+    a = np.empty(n.value)
+    check(lib.qca_chebyshev_plan(z, tol, as_double_ptr(a), n.value, C.byref(n)))
+    return a
+
+
+def plan_passes(local_bits: int) -> list[dict]:
+    n = C.c_int32()
+    check(lib.qca_plan_passes(local_bits, None, 0, C.byref(n)))
+    buf = (PassStruct * n.value)()
+    check(lib.qca_plan_passes(local_bits, buf, n.value, C.byref(n)))
+    return [dict(low_bits=p.low_bits, high_start=p.high_start, high_bits=p.high_bits, flip_mask=p.flip_mask)
+            for p in buf]
+
+
+def measure_finish(sums: np.ndarray, ncells: int):
+    sums = np.ascontiguousarray(sums, dtype=np.float64)
+    pop, dpop, ent = np.empty(ncells), np.empty(ncells), np.empty(ncells)
+    bonds = np.empty(ncells + 1)
+    check(lib.qca_measure_finish(as_double_ptr(sums), ncells, as_double_ptr(pop), as_double_ptr(dpop),
+                                 as_double_ptr(ent), as_double_ptr(bonds)))
+    return pop, dpop, ent, bonds
+
+
+# ---------------------------------------------------------------------------
+# Exact engine handle
+# ---------------------------------------------------------------------------
+class ExactEngine:
+    """Thin owner of a ``qca_exact_t`` (see include/qca_b200.h)."""
+
+    def __init__(self, rules, device: int = 0, world_size: int = 1, rank: int = 0, flags: int = 0,
+                 stream: int | None = None):
+        self._h = C.c_void_p()
+        self.ncells = int(rules.ncells)
+        rs = rule_struct(rules)
+        check(lib.qca_exact_create(C.byref(self._h), C.byref(rs), device, world_size, rank, flags,
+                                   C.c_void_p(stream) if stream else None))
+        self.local_amps = int(lib.qca_exact_local_amps(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.qca_exact_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host_c128(buf) -> np.ndarray:
+        arr = np.ascontiguousarray(buf, dtype=np.complex128)
+        return arr
+
+    def set_state(self, psi) -> None:
+        arr = self._host_c128(psi).reshape(-1)
+        check(lib.qca_exact_set_state(self._h, C.c_void_p(arr.ctypes.data), arr.size))
+
+    def set_state_ptr(self, ptr: int, namps: int) -> None:
+        """Upload from a raw host pointer (e.g. pinned memory), interleaved complex128."""
+        check(lib.qca_exact_set_state(self._h, C.c_void_p(ptr), namps))
+
+    def set_product_state(self, plist) -> None:
+        p = np.ascontiguousarray(plist, dtype=np.float64)
+        check(lib.qca_exact_set_product_state(self._h, as_double_ptr(p), p.size))
+
+    def get_state(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.local_amps, dtype=np.complex128)
+        assert out.dtype == np.complex128 and out.flags.c_contiguous and out.size == self.local_amps
+        check(lib.qca_exact_get_state(self._h, C.c_void_p(out.ctypes.data), out.size))
+        return out
+
+    def get_state_ptr(self, ptr: int, namps: int) -> None:
+        check(lib.qca_exact_get_state(self._h, C.c_void_p(ptr), namps))
+
+    def step(self, step_size: float, nsteps: int = 1) -> None:
+        check(lib.qca_exact_step(self._h, float(step_size), int(nsteps)))
+
+    def measure(self):
+        n = self.ncells
+        pop, dpop, ent, bonds = np.empty(n), np.empty(n), np.empty(n), np.empty(n + 1)
+        check(lib.qca_exact_measure(self._h, as_double_ptr(pop), as_double_ptr(dpop), as_double_ptr(ent),
+                                    as_double_ptr(bonds)))
+        return pop, dpop, ent, bonds
+
+    def measure_partial(self) -> np.ndarray:
+        sums = np.empty(4 * self.ncells)
+        check(lib.qca_exact_measure_partial(self._h, as_double_ptr(sums)))
+        return sums
+
+    def apply_h(self, vec) -> np.ndarray:
+        arr = self._host_c128(vec).reshape(-1)
+        out = np.empty_like(arr)
+        check(lib.qca_exact_apply_h(self._h, C.c_void_p(arr.ctypes.data), C.c_void_p(out.ctypes.data), arr.size))
+        return out
+
+    def norm2(self) -> float:
+        v = C.c_double()
+        check(lib.qca_exact_norm2(self._h, C.byref(v)))
+        return v.value
+
+    def stats(self) -> dict:
+        st = ExactStats()
+        check(lib.qca_exact_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def reset_stats(self) -> None:
+        check(lib.qca_exact_reset_stats(self._h))

@@ -1,0 +1,756 @@
+// Exact (state-vector) evolution engine: matrix-free rule operator, Clenshaw-Chebyshev
+// stepper, fused measurement.  Replaces algorithms/exact.py + lautils.calculate_U +
+// MPO.as_matrix + MPS.measure of the reference for the `--algorithm exact` path.
+//
+// Representation (DESIGN.md "parity rotation"): the resident state is phi with
+//     psi[x] = g * i^popcount(x) * phi[x],   g in {1, i}
+// held as separate real planes (SoA).  In this frame exp(-i t H) = exp(t K) with the real
+// antisymmetric K[x, x^b_c] = P_c(x) * (+1 if cell c dead in x else -1), so re and im planes
+// evolve independently under real arithmetic, and a state whose rotated form is real (every
+// basis state) needs ONE plane.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "qca_common.cuh"
+#include "qca_plan.h"
+
+namespace qca {
+
+constexpr int kPassThreads = 256;
+constexpr int kMaxWorld = 8;
+
+// ---------------------------------------------------------------------------
+// Tile-pass kernel
+// ---------------------------------------------------------------------------
+struct PassArgs {
+    const double* in[2];     // vector the operator is applied to (plane 0/1)
+    const double* a_src[2];  // optional: + alpha * a_src[x]
+    const double* c_src[2];  // optional: + beta * c_src[x]   (may alias out)
+    double* out[2];
+    double alpha, beta, gamma;
+    unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
+    unsigned long long prefix;     // rank << local_bits: the sharded qubits of this rank
+    unsigned long long ntiles;
+    int low_bits, high_start, high_bits;  // tile = bits [0,low) U [high_start, high_start+high_bits)
+    int distance;
+    unsigned interval_mask;
+};
+
+template <typename I>
+__global__ void __launch_bounds__(kPassThreads) pass_kernel(const PassArgs a) {
+    extern __shared__ double tile[];
+    const int plane = blockIdx.y;
+    const double* __restrict__ in = a.in[plane];
+    const double* __restrict__ asrc = a.a_src[plane];
+    const double* csrc = a.c_src[plane];
+    double* out = a.out[plane];
+    const int L = a.low_bits, H0 = a.high_start, M = a.high_bits;
+    const int T = L + M;
+    const unsigned tile_elems = 1u << T;
+    const unsigned low_mask = (1u << L) - 1u;
+    const int gap = H0 - L;
+
+    for (unsigned long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const I t_lo = (I)(t & ((1ull << gap) - 1ull));
+        const I t_hi = (I)(t >> gap);
+        const I base = (t_lo << L) | (t_hi << (H0 + M));
+        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            tile[y] = in[x];
+        }
+        __syncthreads();
+        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            const I act = activity_word<I>(x | (I)a.prefix, a.distance, a.interval_mask) & (I)a.flip_mask;
+            double acc = 0.0;
+            for (int q = 0; q < T; ++q) {
+                const int g = q < L ? q : H0 + (q - L);
+                if ((act >> g) & 1) {
+                    const double v = tile[y ^ (1u << q)];
+                    acc += ((y >> q) & 1u) ? -v : v;  // K = sum_c P_c (sigma^-  -  sigma^+)_c
+                }
+            }
+            double r = a.gamma * acc;
+            if (asrc) r += a.alpha * asrc[x];
+            if (csrc) r += a.beta * csrc[x];
+            out[x] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// out = alpha * src
+__global__ void scale_kernel(double* __restrict__ out, const double* __restrict__ src, double alpha,
+                             unsigned long long n) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = alpha * src[i];
+}
+
+// ---------------------------------------------------------------------------
+// Host <-> device state conversion
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_abs(unsigned long long* slot, double v) {
+    atomicMax(slot, (unsigned long long)__double_as_longlong(fabs(v)));
+}
+
+// staged: interleaved psi.  phi = i^{-popcount} psi, exact (swaps and negations only).
+__global__ void unpack_rotate_kernel(const double2* __restrict__ staged, double* __restrict__ re,
+                                     double* __restrict__ im, unsigned long long offset,
+                                     unsigned long long count, unsigned long long prefix,
+                                     unsigned long long* maxabs) {
+    double mre = 0.0, mim = 0.0;
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        const unsigned long long x = offset + i;
+        const double2 p = staged[i];
+        double a, b;
+        switch (__popcll(x | prefix) & 3) {
+            case 0: a = p.x; b = p.y; break;
+            case 1: a = p.y; b = -p.x; break;
+            case 2: a = -p.x; b = -p.y; break;
+            default: a = -p.y; b = p.x; break;
+        }
+        re[x] = a; im[x] = b;
+        mre = fmax(mre, fabs(a)); mim = fmax(mim, fabs(b));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mre = fmax(mre, __shfl_xor_sync(0xffffffffu, mre, o));
+        mim = fmax(mim, __shfl_xor_sync(0xffffffffu, mim, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mre > 0.0) atomic_max_abs(maxabs + 0, mre);
+        if (mim > 0.0) atomic_max_abs(maxabs + 1, mim);
+    }
+}
+
+// staged[i] = (gr + i gi) * i^{popcount + extra} * (re + i im)
+__global__ void pack_rotate_kernel(double2* __restrict__ staged, const double* __restrict__ re,
+                                   const double* __restrict__ im, unsigned long long offset,
+                                   unsigned long long count, unsigned long long prefix, int extra_quarter) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        const unsigned long long x = offset + i;
+        const double a = re[x], b = im ? im[x] : 0.0;
+        double2 p;
+        switch ((__popcll(x | prefix) + extra_quarter) & 3) {
+            case 0: p.x = a; p.y = b; break;
+            case 1: p.x = -b; p.y = a; break;
+            case 2: p.x = -a; p.y = -b; break;
+            default: p.x = b; p.y = -a; break;
+        }
+        staged[i] = p;
+    }
+}
+
+// Product state (mps.py:35-52 + 194-208) directly in the rotated frame.
+// amp[2*cell + s] = sqrt(1-p) (s=0) or sqrt(p) (s=1); cell 0 is the top bit.
+__global__ void product_state_kernel(double* __restrict__ re, double* __restrict__ im,
+                                     const double* __restrict__ amp, int ncells, int local_bits,
+                                     unsigned long long prefix, unsigned long long* maxabs) {
+    double mre = 0.0, mim = 0.0;
+    const unsigned long long n = 1ull << local_bits;
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned long long xf = i | prefix;
+        double v = 1.0;
+        for (int cell = 0; cell < ncells; ++cell) {
+            const int s = (int)((xf >> (ncells - 1 - cell)) & 1ull);
+            v *= amp[2 * cell + s];
+        }
+        double a, b;
+        switch (__popcll(xf) & 3) {
+            case 0: a = v; b = 0.0; break;
+            case 1: a = 0.0; b = -v; break;
+            case 2: a = -v; b = 0.0; break;
+            default: a = 0.0; b = v; break;
+        }
+        re[i] = a; im[i] = b;
+        mre = fmax(mre, fabs(a)); mim = fmax(mim, fabs(b));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mre = fmax(mre, __shfl_xor_sync(0xffffffffu, mre, o));
+        mim = fmax(mim, __shfl_xor_sync(0xffffffffu, mim, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mre > 0.0) atomic_max_abs(maxabs + 0, mre);
+        if (mim > 0.0) atomic_max_abs(maxabs + 1, mim);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Measurement: for qubit `bit` the four sums over pairs (x0, x1 = x0 | 1<<bit)
+//   s0 = sum |phi[x0]|^2, s1 = sum |phi[x1]|^2, w = sum phi[x0] conj(phi[x1]).
+// (rho_01 of the reference's density matrix, mps.py:122-126, is -i*w: same modulus.)
+// Per-block partials, then a fixed-order final reduction: deterministic.
+// ---------------------------------------------------------------------------
+constexpr int kMeasureThreads = 256;
+
+__global__ void __launch_bounds__(kMeasureThreads)
+measure_pairs_kernel(const double* __restrict__ re0, const double* __restrict__ im0,
+                     const double* __restrict__ re1, const double* __restrict__ im1, int bit,
+                     unsigned long long npairs, double* __restrict__ partials) {
+    double s0 = 0.0, s1 = 0.0, wr = 0.0, wi = 0.0;
+    unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; j < npairs; j += stride) {
+        unsigned long long x0, x1;
+        if (bit >= 0) {
+            x0 = ((j >> bit) << (bit + 1)) | (j & ((1ull << bit) - 1ull));
+            x1 = x0 | (1ull << bit);
+        } else {
+            x0 = x1 = j;  // partner vector is a different buffer (sharded qubit)
+        }
+        const double a0 = re0[x0], a1 = re1[x1];
+        const double b0 = im0 ? im0[x0] : 0.0, b1 = im1 ? im1[x1] : 0.0;
+        s0 += a0 * a0 + b0 * b0;
+        s1 += a1 * a1 + b1 * b1;
+        wr += a0 * a1 + b0 * b1;
+        wi += b0 * a1 - a0 * b1;
+    }
+    __shared__ double sh[4][kMeasureThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        wr += __shfl_xor_sync(0xffffffffu, wr, o);
+        wi += __shfl_xor_sync(0xffffffffu, wi, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; sh[2][warp] = wr; sh[3][warp] = wi; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < kMeasureThreads / 32; ++w) t += sh[threadIdx.x][w];
+        partials[4ull * blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks,
+                                       double* __restrict__ out4) {
+    // one warp per component; fixed summation order
+    const int comp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double t = 0.0;
+    for (int b = lane; b < nblocks; b += 32) t += partials[4ull * b + comp];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) out4[comp] = t;
+}
+
+// ---------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------
+struct Engine {
+    qca_rule_t rule{};
+    int device = 0, world = 1, rank = 0, rank_bits = 0, local_bits = 0;
+    uint32_t flags = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned long long namps = 0, prefix = 0;
+    double* plane[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    int cur = 0;          // vector index of the resident state
+    int nplanes = 0;      // 0: no state yet
+    int g_quarter = 0;    // psi = i^g_quarter * D * phi
+    double bound = 0.0;   // spectral bound R
+    std::vector<qca_pass_t> passes;
+    double2* staging = nullptr;
+    unsigned long long staging_amps = 0;
+    unsigned long long* d_maxabs = nullptr;
+    double* d_partials = nullptr;
+    double* d_sums = nullptr;
+    double* d_amp = nullptr;
+    int measure_blocks = 0;
+    int num_sms = 148;
+    // stats
+    qca_exact_stats_t st{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    int max_smem_set = 0;
+
+    size_t plane_bytes() const { return (size_t)namps * sizeof(double); }
+};
+
+static int32_t ensure_plane(Engine* e, int v, int p) {
+    if (e->plane[v][p]) return QCA_OK;
+    cudaError_t err = cudaMalloc(&e->plane[v][p], e->plane_bytes());
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of a %zu-byte state plane failed: %s", e->plane_bytes(), cudaGetErrorString(err));
+        return QCA_ERR_NOMEM;
+    }
+    e->st.device_bytes += (double)e->plane_bytes();
+    return QCA_OK;
+}
+
+static void release_plane(Engine* e, int v, int p) {
+    if (!e->plane[v][p]) return;
+    cudaFree(e->plane[v][p]);
+    e->plane[v][p] = nullptr;
+    e->st.device_bytes -= (double)e->plane_bytes();
+}
+
+static int32_t launch_pass(Engine* e, const qca_pass_t& ps, PassArgs& a) {
+    a.low_bits = ps.low_bits; a.high_start = ps.high_start; a.high_bits = ps.high_bits;
+    a.flip_mask = ps.flip_mask;
+    a.prefix = e->prefix;
+    a.distance = e->rule.distance;
+    a.interval_mask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+    const int T = ps.low_bits + ps.high_bits;
+    a.ntiles = e->namps >> T;
+    const int smem = (int)(sizeof(double) << T);
+    const bool wide = (e->rule.ncells > 31);
+    auto kern = wide ? pass_kernel<unsigned long long> : pass_kernel<unsigned int>;
+    if (smem > e->max_smem_set) {
+        QCA_CUDA(cudaFuncSetAttribute(pass_kernel<unsigned int>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        QCA_CUDA(cudaFuncSetAttribute(pass_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        e->max_smem_set = smem;
+    }
+    unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
+    dim3 grid(gx, e->nplanes, 1);
+    const bool profile = (e->flags & QCA_FLAG_PROFILE) != 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (profile) {
+        QCA_CUDA(cudaEventCreate(&ev0)); QCA_CUDA(cudaEventCreate(&ev1));
+        QCA_CUDA(cudaEventRecord(ev0, e->stream));
+    }
+    kern<<<grid, kPassThreads, smem, e->stream>>>(a);
+    QCA_CUDA(cudaGetLastError());
+    if (profile) {
+        QCA_CUDA(cudaEventRecord(ev1, e->stream));
+        e->prof.emplace_back(ev0, ev1);
+    }
+    // algorithmic bytes: every operand vector once per plane
+    double vecs = 2.0;  // in + out
+    if (a.a_src[0]) vecs += 1.0;
+    if (a.c_src[0]) vecs += 1.0;
+    e->st.pass_bytes += vecs * (double)e->plane_bytes() * e->nplanes;
+    e->st.pass_launches += 1;
+    e->st.kernel_launches += 1;
+    return QCA_OK;
+}
+
+// out = alpha*a + beta*c + gamma * K in      (a, c optional; c may be out)
+static int32_t apply_operator(Engine* e, int v_out, int v_in, int v_a, double alpha, int v_c, double beta,
+                              double gamma) {
+    for (size_t i = 0; i < e->passes.size(); ++i) {
+        PassArgs a{};
+        for (int p = 0; p < 2; ++p) {
+            a.in[p] = e->plane[v_in][p];
+            a.out[p] = e->plane[v_out][p];
+            if (i == 0) {
+                a.a_src[p] = v_a >= 0 ? e->plane[v_a][p] : nullptr;
+                a.c_src[p] = v_c >= 0 ? e->plane[v_c][p] : nullptr;
+            } else {
+                a.a_src[p] = nullptr;
+                a.c_src[p] = e->plane[v_out][p];
+            }
+        }
+        a.alpha = (i == 0) ? alpha : 0.0;
+        a.beta = (i == 0) ? beta : 1.0;
+        a.gamma = gamma;
+        QCA_CHECK(launch_pass(e, e->passes[i], a));
+    }
+    return QCA_OK;
+}
+
+static int32_t launch_scale(Engine* e, int v_out, int v_src, double alpha) {
+    for (int p = 0; p < e->nplanes; ++p) {
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((e->namps + 255) / 256, (unsigned long long)e->num_sms * 16);
+        scale_kernel<<<blocks, 256, 0, e->stream>>>(e->plane[v_out][p], e->plane[v_src][p], alpha, e->namps);
+        QCA_CUDA(cudaGetLastError());
+        e->st.kernel_launches += 1;
+    }
+    return QCA_OK;
+}
+
+static int32_t ensure_work_planes(Engine* e) {
+    for (int v = 0; v < 3; ++v)
+        for (int p = 0; p < e->nplanes; ++p) QCA_CHECK(ensure_plane(e, v, p));
+    return QCA_OK;
+}
+
+// phi <- exp(t K) phi by Clenshaw summation of sum_k a_k U_k(K/R) phi with
+// U_{k+1} = 2x U_k + U_{k-1}:  B_k = a_k phi + (2/R) K B_{k+1} + B_{k+2},
+// phi' = a_0 phi + (1/R) K B_1 + B_2.
+static int32_t step_once(Engine* e, double step_size) {
+    const double t = (M_PI / 2.0) * step_size;
+    if (t == 0.0) return QCA_OK;
+    const double sgn = t < 0.0 ? -1.0 : 1.0;
+    const double z = e->bound * fabs(t);
+    std::vector<double> a;
+    QCA_CHECK(chebyshev_plan(z, 1e-15, a));
+    const int K = (int)a.size() - 1;  // >= 1
+    e->st.last_terms = K + 1;
+    QCA_CHECK(ensure_work_planes(e));
+    const int P = e->cur;
+    int X = (P + 1) % 3, Y = (P + 2) % 3;
+    const double R = e->bound;
+    QCA_CHECK(launch_scale(e, X, P, a[K]));  // B_K
+    for (int k = K - 1; k >= 1; --k) {
+        const bool first = (k == K - 1);  // B_{K+1} = 0
+        QCA_CHECK(apply_operator(e, Y, X, P, a[k], first ? -1 : Y, 1.0, sgn * 2.0 / R));
+        std::swap(X, Y);
+    }
+    QCA_CHECK(apply_operator(e, Y, X, P, a[0], (K == 1) ? -1 : Y, 1.0, sgn / R));
+    e->cur = Y;
+    return QCA_OK;
+}
+
+static int32_t finish_profile(Engine* e) {
+    if (e->prof.empty()) return QCA_OK;
+    QCA_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto& pr : e->prof) {
+        float ms = 0.f;
+        QCA_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        e->st.profiled_pass_ms += ms;
+        e->st.profiled_pass_launches += 1;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    e->prof.clear();
+    return QCA_OK;
+}
+
+// After a state upload: decide the number of planes from the exact maxima.
+static int32_t settle_planes(Engine* e) {
+    unsigned long long h[2];
+    QCA_CUDA(cudaMemcpyAsync(h, e->d_maxabs, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    QCA_CUDA(cudaStreamSynchronize(e->stream));
+    const bool has_re = h[0] != 0, has_im = h[1] != 0;
+    e->g_quarter = 0;
+    if (e->world > 1 || (e->flags & QCA_FLAG_FORCE_COMPLEX) || (has_re && has_im)) {
+        e->nplanes = 2;
+    } else if (has_im) {  // purely imaginary rotated state: psi = i * D * (im plane)
+        std::swap(e->plane[e->cur][0], e->plane[e->cur][1]);
+        e->g_quarter = 1;
+        e->nplanes = 1;
+    } else {
+        e->nplanes = 1;
+    }
+    if (e->nplanes == 1) release_plane(e, e->cur, 1);
+    return QCA_OK;
+}
+
+static int32_t prepare_upload(Engine* e) {
+    // keep only the state vector's planes while uploading; work planes come back lazily
+    QCA_CHECK(ensure_plane(e, e->cur, 0));
+    QCA_CHECK(ensure_plane(e, e->cur, 1));
+    QCA_CUDA(cudaMemsetAsync(e->d_maxabs, 0, 2 * sizeof(unsigned long long), e->stream));
+    return QCA_OK;
+}
+
+static int32_t ensure_staging(Engine* e) {
+    if (e->staging) return QCA_OK;
+    e->staging_amps = std::min<unsigned long long>(e->namps, 1ull << 22);
+    QCA_CUDA(cudaMalloc(&e->staging, e->staging_amps * sizeof(double2)));
+    e->st.device_bytes += (double)(e->staging_amps * sizeof(double2));
+    return QCA_OK;
+}
+
+static unsigned stream_blocks(Engine* e, unsigned long long n) {
+    return (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((n + 255) / 256, (unsigned long long)e->num_sms * 16));
+}
+
+static int32_t upload_vector(Engine* e, int v, const double* host, bool track) {
+    QCA_CHECK(ensure_staging(e));
+    for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
+        const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
+        QCA_CUDA(cudaMemcpyAsync(e->staging, host + 2 * off, cnt * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
+        unpack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
+            e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->prefix, e->d_maxabs + (track ? 0 : 2));
+        QCA_CUDA(cudaGetLastError());
+        e->st.kernel_launches += 1;
+    }
+    return QCA_OK;
+}
+
+static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter) {
+    QCA_CHECK(ensure_staging(e));
+    for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
+        const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
+        pack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
+            e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->prefix, extra_quarter);
+        QCA_CUDA(cudaGetLastError());
+        e->st.kernel_launches += 1;
+        QCA_CUDA(cudaMemcpyAsync(host + 2 * off, e->staging, cnt * sizeof(double2), cudaMemcpyDeviceToHost, e->stream));
+        // the staging buffer is reused by the next chunk
+        QCA_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return QCA_OK;
+}
+
+static int32_t measure_partial(Engine* e, double* sums) {
+    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "measure before a state was set");
+    const int n = e->rule.ncells;
+    const double* re = e->plane[e->cur][0];
+    const double* im = e->nplanes == 2 ? e->plane[e->cur][1] : nullptr;
+    QCA_CUDA(cudaMemsetAsync(e->d_sums, 0, 4 * n * sizeof(double), e->stream));
+    for (int bit = 0; bit < e->local_bits; ++bit) {
+        const int cell = n - 1 - bit;
+        const unsigned long long npairs = e->namps >> 1;
+        const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + kMeasureThreads - 1) / kMeasureThreads, (unsigned long long)e->measure_blocks));
+        measure_pairs_kernel<<<blocks, kMeasureThreads, 0, e->stream>>>(re, im, re, im, bit, npairs, e->d_partials);
+        QCA_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<1, 128, 0, e->stream>>>(e->d_partials, blocks, e->d_sums + 4 * cell);
+        QCA_CUDA(cudaGetLastError());
+        e->st.kernel_launches += 2;
+    }
+    QCA_CUDA(cudaMemcpyAsync(sums, e->d_sums, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    QCA_CUDA(cudaStreamSynchronize(e->stream));
+    return QCA_OK;
+}
+
+}  // namespace qca
+
+using qca::Engine;
+
+struct qca_exact {
+    Engine e;
+};
+
+extern "C" {
+
+int32_t qca_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t device, int32_t world_size,
+                         int32_t rank, uint32_t flags, void* stream) {
+    QCA_REQUIRE(out != nullptr, QCA_ERR_ARG, "out handle is NULL");
+    *out = nullptr;
+    QCA_CHECK(qca::validate_rule(rule));
+    QCA_REQUIRE(world_size == 1 || world_size == 2 || world_size == 4 || world_size == 8, QCA_ERR_ARG,
+                "world_size must be 1, 2, 4 or 8 (got %d)", world_size);
+    QCA_REQUIRE(rank >= 0 && rank < world_size, QCA_ERR_ARG, "rank %d outside world of %d", rank, world_size);
+    int rank_bits = 0;
+    while ((1 << rank_bits) < world_size) ++rank_bits;
+    QCA_REQUIRE(rule->ncells - rank_bits >= 1, QCA_ERR_ARG, "ncells %d too small for %d ranks", rule->ncells, world_size);
+    QCA_REQUIRE(world_size == 1, QCA_ERR_UNSUPPORTED, "multi-GPU sharding is not wired up yet");
+    int ndev = 0;
+    QCA_CUDA(cudaGetDeviceCount(&ndev));
+    QCA_REQUIRE(device >= 0 && device < ndev, QCA_ERR_CUDA, "device %d not present (%d visible)", device, ndev);
+    QCA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QCA_CUDA(cudaGetDeviceProperties(&prop, device));
+    QCA_REQUIRE(prop.major >= 10, QCA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+
+    qca_exact* h = new qca_exact();
+    Engine* e = &h->e;
+    e->rule = *rule; e->device = device; e->world = world_size; e->rank = rank; e->rank_bits = rank_bits;
+    e->local_bits = rule->ncells - rank_bits;
+    e->namps = 1ull << e->local_bits;
+    e->prefix = (unsigned long long)rank << e->local_bits;
+    e->flags = flags;
+    e->num_sms = prop.multiProcessorCount;
+    e->bound = qca::spectral_bound(*rule);
+    qca::plan_passes(e->local_bits, e->passes);
+    e->st.spectral_bound = e->bound;
+    e->st.passes_per_apply = (int32_t)e->passes.size();
+    e->st.local_bits = e->local_bits;
+    if (stream) { e->stream = (cudaStream_t)stream; e->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            qca::set_error("cudaStreamCreate failed"); delete h; return QCA_ERR_CUDA;
+        }
+        e->own_stream = true;
+    }
+    e->measure_blocks = e->num_sms * 8;
+    bool ok = cudaMalloc(&e->d_maxabs, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&e->d_partials, 4ull * e->measure_blocks * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&e->d_sums, 4ull * rule->ncells * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
+    if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
+    *out = h;
+    return QCA_OK;
+}
+
+int32_t qca_exact_destroy(qca_exact_t h) {
+    if (!h) return QCA_OK;
+    Engine* e = &h->e;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& pr : e->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->plane[v][p]) cudaFree(e->plane[v][p]);
+    if (e->staging) cudaFree(e->staging);
+    if (e->d_maxabs) cudaFree(e->d_maxabs);
+    if (e->d_partials) cudaFree(e->d_partials);
+    if (e->d_sums) cudaFree(e->d_sums);
+    if (e->d_amp) cudaFree(e->d_amp);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete h;
+    return QCA_OK;
+}
+
+uint64_t qca_exact_local_amps(qca_exact_t h) { return h ? h->e.namps : 0; }
+
+int32_t qca_exact_set_state(qca_exact_t h, const double* psi, uint64_t namps) {
+    QCA_REQUIRE(h && psi, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(namps == e->namps, QCA_ERR_ARG, "state has %llu amplitudes, engine holds %llu",
+                (unsigned long long)namps, e->namps);
+    QCA_CUDA(cudaSetDevice(e->device));
+    QCA_CHECK(qca::prepare_upload(e));
+    QCA_CHECK(qca::upload_vector(e, e->cur, psi, true));
+    return qca::settle_planes(e);
+}
+
+int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_t ncells) {
+    QCA_REQUIRE(h && p_alive, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(ncells == e->rule.ncells, QCA_ERR_ARG, "plist has %d entries, rule has %d cells", ncells, e->rule.ncells);
+    std::vector<double> amp(2 * ncells);
+    for (int c = 0; c < ncells; ++c) {
+        QCA_REQUIRE(p_alive[c] >= 0.0 && p_alive[c] <= 1.0, QCA_ERR_ARG, "p_alive[%d] = %g outside [0,1]", c, p_alive[c]);
+        amp[2 * c] = sqrt(1.0 - p_alive[c]);
+        amp[2 * c + 1] = sqrt(p_alive[c]);
+    }
+    QCA_CUDA(cudaSetDevice(e->device));
+    QCA_CHECK(qca::prepare_upload(e));
+    QCA_CUDA(cudaMemcpyAsync(e->d_amp, amp.data(), amp.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    qca::product_state_kernel<<<qca::stream_blocks(e, e->namps), 256, 0, e->stream>>>(
+        e->plane[e->cur][0], e->plane[e->cur][1], e->d_amp, ncells, e->local_bits, e->prefix, e->d_maxabs);
+    QCA_CUDA(cudaGetLastError());
+    e->st.kernel_launches += 1;
+    QCA_CUDA(cudaStreamSynchronize(e->stream));  // amp is a host temporary
+    return qca::settle_planes(e);
+}
+
+int32_t qca_exact_get_state(qca_exact_t h, double* psi, uint64_t namps) {
+    QCA_REQUIRE(h && psi, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "get_state before a state was set");
+    QCA_REQUIRE(namps == e->namps, QCA_ERR_ARG, "buffer has %llu amplitudes, engine holds %llu",
+                (unsigned long long)namps, e->namps);
+    QCA_CUDA(cudaSetDevice(e->device));
+    return qca::download_vector(e, e->cur, psi, e->g_quarter);
+}
+
+int32_t qca_exact_step(qca_exact_t h, double step_size, int32_t nsteps) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "step before a state was set");
+    QCA_REQUIRE(nsteps >= 0, QCA_ERR_ARG, "nsteps must be >= 0");
+    QCA_REQUIRE(isfinite(step_size), QCA_ERR_ARG, "step_size must be finite");
+    QCA_CUDA(cudaSetDevice(e->device));
+    for (int s = 0; s < nsteps; ++s) QCA_CHECK(qca::step_once(e, step_size));
+    return QCA_OK;
+}
+
+int32_t qca_exact_measure_partial(qca_exact_t h, double* sums) {
+    QCA_REQUIRE(h && sums, QCA_ERR_ARG, "NULL argument");
+    QCA_CUDA(cudaSetDevice(h->e.device));
+    return qca::measure_partial(&h->e, sums);
+}
+
+int32_t qca_measure_finish(const double* sums, int32_t ncells, double* population, double* d_population,
+                           double* entropy, double* bond_dims) {
+    QCA_REQUIRE(sums && ncells >= 1, QCA_ERR_ARG, "bad arguments");
+    for (int c = 0; c < ncells; ++c) {
+        const double s0 = sums[4 * c], s1 = sums[4 * c + 1], wr = sums[4 * c + 2], wi = sums[4 * c + 3];
+        if (population) population[c] = s1;
+        if (d_population) d_population[c] = nearbyint(s1);  // np.round: half to even
+        if (entropy) {
+            const double mean = 0.5 * (s0 + s1), half = 0.5 * (s0 - s1);
+            const double rad = sqrt(half * half + wr * wr + wi * wi);
+            const double lam[2] = {mean + rad, mean - rad};
+            double ent = 0.0;
+            for (double l : lam) if (l > 0.0) ent -= l * log2(l);
+            entropy[c] = ent;
+        }
+    }
+    if (bond_dims)
+        for (int i = 0; i <= ncells; ++i) bond_dims[i] = ldexp(1.0, std::min(i, ncells - i));
+    return QCA_OK;
+}
+
+int32_t qca_exact_measure(qca_exact_t h, double* population, double* d_population, double* entropy,
+                          double* bond_dims) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    QCA_REQUIRE(h->e.world == 1, QCA_ERR_STATE, "sharded engine: use measure_partial + all-reduce + qca_measure_finish");
+    std::vector<double> sums(4 * h->e.rule.ncells);
+    QCA_CHECK(qca_exact_measure_partial(h, sums.data()));
+    return qca_measure_finish(sums.data(), h->e.rule.ncells, population, d_population, entropy, bond_dims);
+}
+
+int32_t qca_exact_apply_h(qca_exact_t h, const double* in, double* out, uint64_t namps) {
+    QCA_REQUIRE(h && in && out, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(namps == e->namps, QCA_ERR_ARG, "vector has %llu amplitudes, engine holds %llu",
+                (unsigned long long)namps, e->namps);
+    QCA_CUDA(cudaSetDevice(e->device));
+    const int X = (e->cur + 1) % 3, Y = (e->cur + 2) % 3;
+    const int saved_planes = e->nplanes;
+    e->nplanes = 2;
+    int32_t rc = QCA_OK;
+    do {
+        if ((rc = qca::ensure_plane(e, X, 0)) || (rc = qca::ensure_plane(e, X, 1)) ||
+            (rc = qca::ensure_plane(e, Y, 0)) || (rc = qca::ensure_plane(e, Y, 1))) break;
+        if ((rc = qca::upload_vector(e, X, in, false))) break;
+        // H psi = D (i K) D^-1 psi: apply K in the rotated frame, one extra quarter turn on the way out
+        if ((rc = qca::apply_operator(e, Y, X, -1, 0.0, -1, 0.0, 1.0))) break;
+        rc = qca::download_vector(e, Y, out, 1);
+    } while (0);
+    e->nplanes = saved_planes;
+    if (saved_planes < 2) { qca::release_plane(e, X, 1); qca::release_plane(e, Y, 1); }
+    return rc;
+}
+
+int32_t qca_exact_norm2(qca_exact_t h, double* norm2) {
+    QCA_REQUIRE(h && norm2, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "norm before a state was set");
+    QCA_CUDA(cudaSetDevice(e->device));
+    const double* re = e->plane[e->cur][0];
+    const double* im = e->nplanes == 2 ? e->plane[e->cur][1] : nullptr;
+    double hsum[4];
+    if (e->local_bits == 0) { *norm2 = 0; return QCA_OK; }
+    const unsigned long long npairs = e->namps >> 1;
+    const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + qca::kMeasureThreads - 1) / qca::kMeasureThreads, (unsigned long long)e->measure_blocks));
+    qca::measure_pairs_kernel<<<blocks, qca::kMeasureThreads, 0, e->stream>>>(re, im, re, im, 0, npairs, e->d_partials);
+    QCA_CUDA(cudaGetLastError());
+    qca::reduce_partials_kernel<<<1, 128, 0, e->stream>>>(e->d_partials, blocks, e->d_sums);
+    QCA_CUDA(cudaGetLastError());
+    e->st.kernel_launches += 2;
+    QCA_CUDA(cudaMemcpyAsync(hsum, e->d_sums, sizeof(hsum), cudaMemcpyDeviceToHost, e->stream));
+    QCA_CUDA(cudaStreamSynchronize(e->stream));
+    *norm2 = hsum[0] + hsum[1];
+    return QCA_OK;
+}
+
+int32_t qca_exact_get_stats(qca_exact_t h, qca_exact_stats_t* out) {
+    QCA_REQUIRE(h && out, QCA_ERR_ARG, "NULL argument");
+    QCA_CUDA(cudaSetDevice(h->e.device));
+    QCA_CHECK(qca::finish_profile(&h->e));
+    h->e.st.planes = h->e.nplanes;
+    *out = h->e.st;
+    return QCA_OK;
+}
+
+int32_t qca_exact_reset_stats(qca_exact_t h) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    QCA_CUDA(cudaSetDevice(h->e.device));
+    QCA_CHECK(qca::finish_profile(&h->e));
+    Engine* e = &h->e;
+    e->st.kernel_launches = 0; e->st.pass_launches = 0; e->st.pass_bytes = 0.0;
+    e->st.profiled_pass_ms = 0.0; e->st.profiled_pass_launches = 0;
+    return QCA_OK;
+}
+
+int32_t qca_exact_ipc_count(qca_exact_t h) { (void)h; return 0; }
+int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IPC_HANDLE_BYTES]) {
+    (void)h; (void)index; (void)handle;
+    qca::set_error("multi-GPU sharding is not wired up yet");
+    return QCA_ERR_UNSUPPORTED;
+}
+int32_t qca_exact_ipc_import(qca_exact_t h, const uint8_t* handles, int32_t world_size, int32_t count) {
+    (void)h; (void)handles; (void)world_size; (void)count;
+    qca::set_error("multi-GPU sharding is not wired up yet");
+    return QCA_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

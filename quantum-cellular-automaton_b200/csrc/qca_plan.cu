@@ -1,0 +1,175 @@
+// Host-only planning: spectral bound, Chebyshev/Bessel coefficients, tile-pass plan.
+// None of these touch the GPU, so the CPU test-suite exercises them through the C ABI.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "qca_common.cuh"
+#include "qca_plan.h"
+
+namespace qca {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int32_t validate_rule(const qca_rule_t* r) {
+    QCA_REQUIRE(r != nullptr, QCA_ERR_ARG, "rule is NULL");
+    QCA_REQUIRE(r->ncells >= 1, QCA_ERR_ARG, "ncells must be >= 1 (got %d)", r->ncells);
+    QCA_REQUIRE(r->distance >= 1, QCA_ERR_ARG, "distance must be >= 1 (got %d)", r->distance);
+    QCA_REQUIRE(r->distance <= 7, QCA_ERR_UNSUPPORTED, "distance > 7 not supported (got %d)", r->distance);
+    QCA_REQUIRE(r->ncells <= 40, QCA_ERR_UNSUPPORTED, "ncells > 40 not supported (got %d)", r->ncells);
+    QCA_REQUIRE(r->act_lo >= 0 && r->act_hi >= r->act_lo, QCA_ERR_ARG,
+                "activation interval [%d,%d) is not a range", r->act_lo, r->act_hi);
+    return QCA_OK;
+}
+
+// Largest number of simultaneously active cells: sliding window of 2d+1 cells,
+// dead cells beyond both ends (mpo.py:181-200).
+double spectral_bound(const qca_rule_t& r) {
+    const int d = r.distance, n = r.ncells;
+    const int wbits = 2 * d + 1;
+    const uint32_t wmask = (1u << wbits) - 1u;
+    const uint32_t imask = interval_mask_of(r.act_lo, r.act_hi);
+    const int NEG = -1000000;
+    std::vector<int> cur(1u << wbits, NEG), nxt(1u << wbits, NEG);
+    cur[0] = 0;
+    for (int i = 0; i < n + d; ++i) {  // append cell i (virtual dead cell when i >= n)
+        std::fill(nxt.begin(), nxt.end(), NEG);
+        for (uint32_t w = 0; w <= wmask; ++w) {
+            if (cur[w] == NEG) continue;
+            for (int c = 0; c <= (i < n ? 1 : 0); ++c) {
+                uint32_t w2 = ((w << 1) | (uint32_t)c) & wmask;
+                int gain = 0;
+                int centre = i - d;  // its whole neighbourhood is now inside the window
+                if (centre >= 0 && centre < n) {
+                    uint32_t nb = w2 & ~(1u << d);
+                    int cnt = __builtin_popcount(nb);
+                    gain = (imask >> cnt) & 1u;
+                }
+                nxt[w2] = std::max(nxt[w2], cur[w] + gain);
+            }
+        }
+        cur.swap(nxt);
+    }
+    int best = 0;
+    for (int v : cur) best = std::max(best, v);
+    return (double)best;
+}
+
+// J_k(z), k = 0..kmax, by Miller's backward recurrence normalised with
+// 1 = J_0 + 2 sum_{k>=1} J_2k.
+static void bessel_j(double z, int kmax, std::vector<long double>& out) {
+    out.assign(kmax + 1, 0.0L);
+    if (z == 0.0) { out[0] = 1.0L; return; }
+    int start = (int)(std::max((double)kmax, z) + 14.0 * cbrt(std::max(z, 1.0)) + 60.0);
+    start += start & 1;
+    long double jp = 0.0L, jc = 1e-300L, norm = 0.0L;
+    const long double zz = z;
+    for (int k = start; k >= 1; --k) {
+        long double jm = (2.0L * k / zz) * jc - jp;  // J_{k-1}
+        jp = jc; jc = jm;
+        if (k - 1 <= kmax) out[k - 1] = jc;
+        if (((k - 1) & 1) == 0) norm += (k - 1 == 0) ? jc : 2.0L * jc;
+        if (fabsl(jc) > 1e250L) {  // rescale
+            const long double s = 1e-250L;
+            jc *= s; jp *= s; norm *= s;
+            for (auto& v : out) v *= s;
+        }
+    }
+    for (auto& v : out) v /= norm;
+}
+
+int32_t chebyshev_plan(double z, double tol, std::vector<double>& a) {
+    QCA_REQUIRE(z >= 0.0 && isfinite(z), QCA_ERR_ARG, "chebyshev z must be finite and >= 0");
+    QCA_REQUIRE(tol > 0.0, QCA_ERR_ARG, "chebyshev tolerance must be > 0");
+    int kmax = (int)(z + 12.0 * cbrt(std::max(z, 1.0)) + 40.0);
+    std::vector<long double> j;
+    bessel_j(z, kmax, j);
+    // keep a[0..n-1] with tail sum_{k>=n} 2|J_k| < tol
+    long double tail = 0.0L;
+    int n = kmax + 1;
+    while (n > 2) {
+        long double t = tail + 2.0L * fabsl(j[n - 1]);
+        if (t >= tol) break;
+        tail = t; --n;
+    }
+    a.resize(n);
+    for (int k = 0; k < n; ++k) a[k] = (double)((k == 0 ? 1.0L : 2.0L) * j[k]);
+    return QCA_OK;
+}
+
+void plan_passes(int local_bits, std::vector<qca_pass_t>& out) {
+    out.clear();
+    const int n = local_bits;
+    int covered = std::min(n, kTileBits);
+    qca_pass_t p0{};
+    p0.low_bits = covered; p0.high_start = covered; p0.high_bits = 0;
+    p0.flip_mask = (covered >= 64) ? ~0ull : ((1ull << covered) - 1ull);
+    out.push_back(p0);
+    // remaining qubits: spread evenly over the fewest passes
+    int rem = n - covered;
+    if (rem <= 0) return;
+    const int per = kTileBits - kMinLowBits;
+    int npass = (rem + per - 1) / per;
+    for (int i = 0; i < npass; ++i) {
+        int m = rem / (npass - i) + ((rem % (npass - i)) ? 1 : 0);
+        qca_pass_t p{};
+        p.low_bits = kTileBits - m;
+        p.high_start = covered;
+        p.high_bits = m;
+        p.flip_mask = ((1ull << m) - 1ull) << covered;
+        out.push_back(p);
+        covered += m; rem -= m;
+    }
+}
+
+}  // namespace qca
+
+extern "C" {
+
+const char* qca_version(void) { return "qca_b200 0.1 (sm_100a)"; }
+const char* qca_last_error(void) { return qca::g_error; }
+
+int32_t qca_spectral_bound(const qca_rule_t* rule, double* bound) {
+    QCA_CHECK(qca::validate_rule(rule));
+    QCA_REQUIRE(bound != nullptr, QCA_ERR_ARG, "bound is NULL");
+    *bound = qca::spectral_bound(*rule);
+    return QCA_OK;
+}
+
+int32_t qca_chebyshev_plan(double z, double tol, double* a, int32_t capacity, int32_t* nterms) {
+    QCA_REQUIRE(nterms != nullptr, QCA_ERR_ARG, "nterms is NULL");
+    std::vector<double> v;
+    QCA_CHECK(qca::chebyshev_plan(z, tol, v));
+    *nterms = (int32_t)v.size();
+    if (a != nullptr) {
+        QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "coefficient buffer too small (%d < %zu)",
+                    capacity, v.size());
+        memcpy(a, v.data(), v.size() * sizeof(double));
+    }
+    return QCA_OK;
+}
+
+int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity, int32_t* npasses) {
+    QCA_REQUIRE(local_bits >= 1 && local_bits <= 40, QCA_ERR_ARG, "local_bits out of range (%d)", local_bits);
+    QCA_REQUIRE(npasses != nullptr, QCA_ERR_ARG, "npasses is NULL");
+    std::vector<qca_pass_t> v;
+    qca::plan_passes(local_bits, v);
+    *npasses = (int32_t)v.size();
+    if (passes != nullptr) {
+        QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "pass buffer too small");
+        memcpy(passes, v.data(), v.size() * sizeof(qca_pass_t));
+    }
+    return QCA_OK;
+}
+
+}  // extern "C"

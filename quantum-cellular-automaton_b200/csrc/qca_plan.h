@@ -1,0 +1,20 @@
+// Host-side planning interface (internal).
+#pragma once
+#include <vector>
+
+#include "qca_b200.h"
+
+namespace qca {
+
+// A tile is 2^kTileBits doubles (64 KiB of shared memory): three CTAs per SM.
+constexpr int kTileBits = 13;
+// Every tile keeps at least 2^kMinLowBits contiguous doubles (128 B) per row so
+// global accesses stay full cache lines.
+constexpr int kMinLowBits = 4;
+
+int32_t validate_rule(const qca_rule_t* r);
+double spectral_bound(const qca_rule_t& r);
+int32_t chebyshev_plan(double z, double tol, std::vector<double>& a);
+void plan_passes(int local_bits, std::vector<qca_pass_t>& out);
+
+}  // namespace qca

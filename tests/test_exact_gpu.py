@@ -1,0 +1,211 @@
+"""GPU parity tests of the exact path, through the C ABI (ctypes) and the Exact plug-in class,
+against (a) the fixtures produced by the unmodified reference, (b) the CPU oracle on seeded
+inputs, (c) size-independent properties at sizes the oracle cannot reach.
+
+Tolerance: 1e-10 absolute on populations and entropies (BASELINE.json north_star); state
+vectors are compared at 1e-11.
+"""
+import numpy as np
+import pytest
+
+import pass_model
+import qca_b200
+import qca_oracle as oracle
+from conftest import golden_names, load_golden
+from qca_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def make_rules(spec):
+    return qca_b200.Rules(spec["ncells"], range(spec["lo"], spec["hi"]), spec["distance"])
+
+
+@pytest.mark.parametrize("name", golden_names("hpsi"))
+def test_apply_h_matches_reference_matrix(name):
+    spec, g = load_golden(name)
+    n = spec["ncells"]
+    rng = np.random.default_rng(spec["seed"])
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    eng = _lib.ExactEngine(make_rules(spec))
+    assert np.abs(eng.apply_h(v) - g["hv"]).max() < 1e-12
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_names("exact"))
+def test_exact_plugin_matches_reference_run(name):
+    """quantum_game.py:82-119 replayed with the B200 Exact in place of the reference's."""
+    spec, g = load_golden(name)
+    rules = make_rules(spec)
+    args = qca_b200.Args(rules=rules, step_size=float(g["effective_step_size"]))
+    algo = qca_b200.Exact(qca_b200.states.make(spec["state"], rules), qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    steps, n = g["population"].shape
+    pop, dpop, sse = np.zeros((steps, n)), np.zeros((steps, n)), np.zeros((steps, n))
+    bond = np.zeros((steps, n + 1))
+    for k in range(steps):
+        algo.measure(pop[k, :], dpop[k, :], sse[k, :], bond[k, :])
+        algo.do_time_step()
+    assert np.abs(pop - g["population"]).max() < TOL
+    assert np.abs(sse - g["single_site_entropy"]).max() < TOL
+    assert np.array_equal(bond, g["bond_dims"])
+    clear = np.abs(g["population"] - 0.5) > 1e-9
+    assert np.array_equal(dpop[clear], g["d_population"][clear])
+    assert np.abs(algo.state_vector() - g["psi_final"]).max() < 1e-11
+    # the psi property hands back an MPS of the same state (exact.py:19-20)
+    mps = algo.psi
+    assert mps.bond_dims == [int(b) for b in g["bond_dims"][0]]
+    assert np.abs(mps.as_vector() - g["psi_final"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("n,d,lo,hi", [(1, 1, 1, 2), (2, 1, 1, 2), (3, 2, 1, 3), (12, 1, 1, 2), (13, 2, 2, 4),
+                                       (14, 1, 1, 3), (16, 3, 2, 5), (18, 2, 2, 4), (20, 1, 1, 2)])
+def test_apply_h_seeded_vs_oracle(n, d, lo, hi):
+    """Random complex vectors, all pass-count regimes (1, 2 and 3 tile passes)."""
+    rng = np.random.default_rng(100 + n)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    eng = _lib.ExactEngine(qca_b200.Rules(n, range(lo, hi), d))
+    got = eng.apply_h(v)
+    if n <= 11:
+        want = oracle.rule_hamiltonian_direct(n, d, lo, hi) @ v
+    else:  # matrix-free numpy restatement, itself checked against the dense oracle in the CPU suite
+        xs = np.arange(1 << n, dtype=np.int64)
+        act = pass_model.activity(xs, n, d, lo, hi)
+        want = np.zeros_like(v)
+        for gbit in range(n):
+            on = ((act >> gbit) & 1).astype(bool)
+            want[on] += v[xs[on] ^ (1 << gbit)]
+    assert np.abs(got - want).max() < 1e-11
+    eng.close()
+
+
+@pytest.mark.parametrize("state", ["single", "blinker", "equal_superposition", "gradient", "all_ket_1"])
+@pytest.mark.parametrize("tau", [1.0, 0.37])
+def test_step_and_measure_vs_oracle(state, tau):
+    n, d, lo, hi = 10, 1, 1, 2
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    algo = qca_b200.Exact(qca_b200.states.make(state, rules), None, qca_b200.Args(rules=rules, step_size=tau))
+    pop_o, dpop_o, ent_o, bond_o, psi_o = oracle.run_exact(state, n, d, lo, hi, tau, 4)
+    for k in range(4):
+        pop, dpop, ent, bond = (np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n + 1))
+        algo.measure(pop, dpop, ent, bond)
+        assert np.abs(pop - pop_o[k]).max() < TOL and np.abs(ent - ent_o[k]).max() < TOL
+        algo.do_time_step()
+    assert np.abs(algo.state_vector() - psi_o).max() < 1e-11
+
+
+def test_general_complex_state_and_forced_complex_agree():
+    n, d, lo, hi = 11, 2, 2, 4
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    rng = np.random.default_rng(5)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    u = oracle.calculate_U(oracle.rule_hamiltonian_direct(n, d, lo, hi), 1.0)
+    eng = _lib.ExactEngine(rules)
+    eng.set_state(psi)
+    assert eng.stats()["planes"] == 2
+    eng.step(1.0, 2)
+    assert np.abs(eng.get_state() - u @ (u @ psi)).max() < 1e-11
+    pop, _, ent, _ = eng.measure()
+    pop_o, _, ent_o, _ = oracle.measure_vector(u @ (u @ psi), n)
+    assert np.abs(pop - pop_o).max() < TOL and np.abs(ent - ent_o).max() < TOL
+    # a basis state runs on one real plane; forcing two planes gives the same answer
+    basis = np.zeros(1 << n, dtype=complex)
+    basis[0b00101010100] = 1.0
+    one = _lib.ExactEngine(rules)
+    two = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_FORCE_COMPLEX)
+    one.set_state(basis), two.set_state(basis)
+    assert one.stats()["planes"] == 1 and two.stats()["planes"] == 2
+    one.step(1.0, 3), two.step(1.0, 3)
+    want = u @ (u @ (u @ basis))
+    assert np.abs(one.get_state() - want).max() < 1e-11
+    assert np.abs(two.get_state() - want).max() < 1e-11
+    # purely imaginary rotated state (odd popcount basis state times i^k) also takes one plane
+    odd = np.zeros(1 << n, dtype=complex)
+    odd[0b00000000111] = -1j
+    one.set_state(odd)
+    assert one.stats()["planes"] == 1
+    assert np.abs(one.get_state() - odd).max() == 0.0
+    one.step(0.5, 1)
+    assert np.abs(one.get_state() - oracle.calculate_U(oracle.rule_hamiltonian_direct(n, d, lo, hi), 0.5) @ odd).max() < 1e-11
+
+
+def test_upload_download_roundtrip_is_exact():
+    rng = np.random.default_rng(9)
+    for n in (1, 4, 13, 17):
+        psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        eng = _lib.ExactEngine(qca_b200.Rules(n, range(1, 2), 1))
+        eng.set_state(psi)
+        assert np.array_equal(eng.get_state(), psi)
+        assert abs(eng.norm2() - np.vdot(psi, psi).real) < 1e-9 * (1 << n)
+        eng.close()
+
+
+@pytest.mark.parametrize("n,d,lo,hi", [(22, 1, 1, 2), (24, 2, 2, 4)])
+def test_properties_beyond_oracle_reach(n, d, lo, hi):
+    """Sizes where no dense reference exists: unitarity, time reversal, step composition,
+    mirror symmetry of a symmetric initial state, and H-moment conservation."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    eng = _lib.ExactEngine(rules)
+    eng.set_product_state(qca_b200.states.plist("triple_blinker", rules))
+    assert eng.stats()["planes"] == 1 and eng.stats()["passes_per_apply"] >= 2
+    pop0, _, ent0, _ = eng.measure()
+    assert np.abs(ent0).max() < 1e-12 and np.array_equal(pop0, np.array(qca_b200.states.plist("triple_blinker", rules)))
+    eng.step(1.0, 2)
+    assert abs(eng.norm2() - 1.0) < 1e-12
+    pop2, _, ent2, _ = eng.measure()
+    if n % 2 == 1:
+        assert np.abs(pop2 - pop2[::-1]).max() < 1e-12
+    # one step of 2.0 == two steps of 1.0
+    eng2 = _lib.ExactEngine(rules)
+    eng2.set_product_state(qca_b200.states.plist("triple_blinker", rules))
+    eng2.step(2.0, 1)
+    popb, _, entb, _ = eng2.measure()
+    assert np.abs(pop2 - popb).max() < TOL and np.abs(ent2 - entb).max() < TOL
+    # time reversal returns to the basis state
+    eng.step(-1.0, 2)
+    popr, _, entr, _ = eng.measure()
+    assert np.abs(popr - pop0).max() < TOL and np.abs(entr).max() < 1e-9
+    eng.close(), eng2.close()
+
+
+def test_symmetric_state_stays_symmetric_odd_chain():
+    rules = qca_b200.Rules(21, range(1, 2), 1)
+    eng = _lib.ExactEngine(rules)
+    eng.set_product_state(qca_b200.states.plist("single", rules))
+    eng.step(1.0, 3)
+    pop, _, ent, _ = eng.measure()
+    assert np.abs(pop - pop[::-1]).max() < 1e-12 and np.abs(ent - ent[::-1]).max() < 1e-11
+
+
+def test_error_behaviour():
+    rules = qca_b200.Rules(6, range(1, 2), 1)
+    eng = _lib.ExactEngine(rules)
+    with pytest.raises(qca_b200.QcaError) as e:
+        eng.step(1.0)
+    assert e.value.code == _lib.QCA_ERR_STATE
+    with pytest.raises(qca_b200.QcaError) as e:
+        eng.set_state(np.zeros(32, dtype=complex))
+    assert e.value.code == _lib.QCA_ERR_ARG
+    with pytest.raises(qca_b200.QcaError):
+        eng.set_product_state([0.5] * 5)
+    with pytest.raises(qca_b200.QcaError):
+        eng.set_product_state([1.5] + [0.0] * 5)
+    other = qca_b200.MPO.hamiltonian_from_rules(qca_b200.Rules(6, range(1, 3), 1))
+    with pytest.raises(ValueError):
+        qca_b200.Exact(qca_b200.states.make("single", rules), other, qca_b200.Args(rules=rules))
+
+
+def test_zero_step_is_identity_and_stats_count_launches():
+    rules = qca_b200.Rules(15, range(1, 2), 1)
+    eng = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_PROFILE)
+    eng.set_product_state(qca_b200.states.plist("blinker", rules))
+    before = eng.get_state()
+    eng.step(0.0, 3)
+    assert np.array_equal(eng.get_state(), before)
+    eng.reset_stats()
+    eng.step(1.0, 1)
+    st = eng.stats()
+    assert st["passes_per_apply"] == 2 and st["last_terms"] > 10
+    assert st["pass_launches"] == (st["last_terms"] - 1) * 2
+    assert st["profiled_pass_launches"] == st["pass_launches"] and st["profiled_pass_ms"] > 0.0
