@@ -172,7 +172,11 @@ def b200_arm(args) -> None:
     if world > 1:
         raise SystemExit("multi-GPU sharding of the exact path is not wired up in this build")
     torch.cuda.set_device(local_rank)
+    # a real (non-default) stream: handle 0 would make the library create its own stream and the
+    # torch events below would not see the kernels
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
     lo, hi = args.activation_interval
     rules = qca_b200.Rules(args.num_cells, range(lo, hi), args.distance)
     plist = qca_b200.states.plist(args.initial_state, rules)

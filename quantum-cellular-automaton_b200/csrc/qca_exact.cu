@@ -16,71 +16,10 @@
 
 #include "qca_common.cuh"
 #include "qca_plan.h"
+#include "qca_pass.cuh"
 
 namespace qca {
 
-constexpr int kPassThreads = 256;
-constexpr int kMaxWorld = 8;
-
-// ---------------------------------------------------------------------------
-// Tile-pass kernel
-// ---------------------------------------------------------------------------
-struct PassArgs {
-    const double* in[2];     // vector the operator is applied to (plane 0/1)
-    const double* a_src[2];  // optional: + alpha * a_src[x]
-    const double* c_src[2];  // optional: + beta * c_src[x]   (may alias out)
-    double* out[2];
-    double alpha, beta, gamma;
-    unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
-    unsigned long long prefix;     // rank << local_bits: the sharded qubits of this rank
-    unsigned long long ntiles;
-    int low_bits, high_start, high_bits;  // tile = bits [0,low) U [high_start, high_start+high_bits)
-    int distance;
-    unsigned interval_mask;
-};
-
-template <typename I>
-__global__ void __launch_bounds__(kPassThreads) pass_kernel(const PassArgs a) {
-    extern __shared__ double tile[];
-    const int plane = blockIdx.y;
-    const double* __restrict__ in = a.in[plane];
-    const double* __restrict__ asrc = a.a_src[plane];
-    const double* csrc = a.c_src[plane];
-    double* out = a.out[plane];
-    const int L = a.low_bits, H0 = a.high_start, M = a.high_bits;
-    const int T = L + M;
-    const unsigned tile_elems = 1u << T;
-    const unsigned low_mask = (1u << L) - 1u;
-    const int gap = H0 - L;
-
-    for (unsigned long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        const I t_lo = (I)(t & ((1ull << gap) - 1ull));
-        const I t_hi = (I)(t >> gap);
-        const I base = (t_lo << L) | (t_hi << (H0 + M));
-        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
-            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
-            tile[y] = in[x];
-        }
-        __syncthreads();
-        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
-            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
-            const I act = activity_word<I>(x | (I)a.prefix, a.distance, a.interval_mask) & (I)a.flip_mask;
-            double acc = 0.0;
-            for (int q = 0; q < T; ++q) {
-                const int g = q < L ? q : H0 + (q - L);
-                if ((act >> g) & 1) {
-                    const double v = tile[y ^ (1u << q)];
-                    acc += ((y >> q) & 1u) ? -v : v;  // K = sum_c P_c (sigma^-  -  sigma^+)_c
-                }
-            }
-            double r = a.gamma * acc;
-            if (asrc) r += a.alpha * asrc[x];
-            if (csrc) r += a.beta * csrc[x];
-            out[x] = r;
-        }
-        __syncthreads();
-    }
-}
 
 // out = alpha * src
 __global__ void scale_kernel(double* __restrict__ out, const double* __restrict__ src, double alpha,
@@ -268,7 +207,9 @@ struct Engine {
     // stats
     qca_exact_stats_t st{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
-    int max_smem_set = 0;
+    // window lookup tables of the fast pass kernel (device), one pair per pass
+    std::vector<unsigned short*> d_tab_lo, d_tab_hi;
+    bool fast_path = false;
 
     size_t plane_bytes() const { return (size_t)namps * sizeof(double); }
 };
@@ -292,22 +233,79 @@ static void release_plane(Engine* e, int v, int p) {
     e->st.device_bytes -= (double)e->plane_bytes();
 }
 
-static int32_t launch_pass(Engine* e, const qca_pass_t& ps, PassArgs& a) {
+// entry[w] = activity of the middle K bits of the (K + 2d)-bit window w
+static std::vector<unsigned short> window_table(int K, int d, uint32_t imask) {
+    std::vector<unsigned short> tab((size_t)1 << (K + 2 * d));
+    for (size_t w = 0; w < tab.size(); ++w) {
+        const unsigned long long act = activity_word<unsigned long long>((unsigned long long)w, d, imask);
+        tab[w] = (unsigned short)((act >> d) & ((1ull << K) - 1ull));
+    }
+    return tab;
+}
+
+static int32_t upload_table(Engine* e, const std::vector<unsigned short>& tab, unsigned short** out) {
+    QCA_CUDA(cudaMalloc(out, tab.size() * sizeof(unsigned short)));
+    QCA_CUDA(cudaMemcpy(*out, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    e->st.device_bytes += (double)(tab.size() * sizeof(unsigned short));
+    return QCA_OK;
+}
+
+// The fast kernel needs full 13-bit tiles and window tables of sane size (distance <= 4).
+static int32_t build_tables(Engine* e) {
+    const int d = e->rule.distance;
+    e->fast_path = (e->local_bits >= kTile) && d <= 4;
+    e->d_tab_lo.assign(e->passes.size(), nullptr);
+    e->d_tab_hi.assign(e->passes.size(), nullptr);
+    if (!e->fast_path) return QCA_OK;
+    const uint32_t imask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+    for (size_t i = 0; i < e->passes.size(); ++i) {
+        const qca_pass_t& ps = e->passes[i];
+        if (ps.high_bits == 0) {
+            QCA_CHECK(upload_table(e, window_table(9 - d, d, imask), &e->d_tab_lo[i]));
+            QCA_CHECK(upload_table(e, window_table(4 + d, d, imask), &e->d_tab_hi[i]));
+        } else {
+            QCA_CHECK(upload_table(e, window_table(ps.high_bits, d, imask), &e->d_tab_hi[i]));
+        }
+    }
+    return QCA_OK;
+}
+
+template <typename I>
+static void (*select_fast_kernel(int L))(const PassArgs) {
+    switch (L) {
+        case 13: return pass_kernel_v2<I, 13, true>;
+        case 12: return pass_kernel_v2<I, 12, false>;
+        case 11: return pass_kernel_v2<I, 11, false>;
+        case 10: return pass_kernel_v2<I, 10, false>;
+        case 9: return pass_kernel_v2<I, 9, false>;
+        case 8: return pass_kernel_v2<I, 8, false>;
+        case 7: return pass_kernel_v2<I, 7, false>;
+        case 6: return pass_kernel_v2<I, 6, false>;
+        case 5: return pass_kernel_v2<I, 5, false>;
+        case 4: return pass_kernel_v2<I, 4, false>;
+        default: return nullptr;
+    }
+}
+
+static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
+    const qca_pass_t& ps = e->passes[pass_index];
     a.low_bits = ps.low_bits; a.high_start = ps.high_start; a.high_bits = ps.high_bits;
     a.flip_mask = ps.flip_mask;
     a.prefix = e->prefix;
     a.distance = e->rule.distance;
     a.interval_mask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+    a.tab_lo = e->d_tab_lo[pass_index];
+    a.tab_hi = e->d_tab_hi[pass_index];
     const int T = ps.low_bits + ps.high_bits;
     a.ntiles = e->namps >> T;
     const int smem = (int)(sizeof(double) << T);
     const bool wide = (e->rule.ncells > 31);
-    auto kern = wide ? pass_kernel<unsigned long long> : pass_kernel<unsigned int>;
-    if (smem > e->max_smem_set) {
-        QCA_CUDA(cudaFuncSetAttribute(pass_kernel<unsigned int>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        QCA_CUDA(cudaFuncSetAttribute(pass_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        e->max_smem_set = smem;
-    }
+    void (*kern)(const PassArgs) = nullptr;
+    if (e->fast_path && T == kTile)
+        kern = wide ? select_fast_kernel<unsigned long long>(ps.low_bits) : select_fast_kernel<unsigned int>(ps.low_bits);
+    const bool fast = kern != nullptr;
+    if (!fast) kern = wide ? pass_kernel_generic<unsigned long long> : pass_kernel_generic<unsigned int>;
+    QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
     dim3 grid(gx, e->nplanes, 1);
     const bool profile = (e->flags & QCA_FLAG_PROFILE) != 0;
@@ -351,7 +349,7 @@ static int32_t apply_operator(Engine* e, int v_out, int v_in, int v_a, double al
         a.alpha = (i == 0) ? alpha : 0.0;
         a.beta = (i == 0) ? beta : 1.0;
         a.gamma = gamma;
-        QCA_CHECK(launch_pass(e, e->passes[i], a));
+        QCA_CHECK(launch_pass(e, i, a));
     }
     return QCA_OK;
 }
@@ -560,6 +558,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
         e->own_stream = true;
     }
     e->measure_blocks = e->num_sms * 8;
+    if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
     bool ok = cudaMalloc(&e->d_maxabs, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&e->d_partials, 4ull * e->measure_blocks * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_sums, 4ull * rule->ncells * sizeof(double)) == cudaSuccess &&
@@ -576,6 +575,8 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& pr : e->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->plane[v][p]) cudaFree(e->plane[v][p]);
+    for (auto* p : e->d_tab_lo) if (p) cudaFree(p);
+    for (auto* p : e->d_tab_hi) if (p) cudaFree(p);
     if (e->staging) cudaFree(e->staging);
     if (e->d_maxabs) cudaFree(e->d_maxabs);
     if (e->d_partials) cudaFree(e->d_partials);

@@ -1,0 +1,224 @@
+// Tile-pass kernels of the rule operator K (see qca_exact.cu header for the rotated frame).
+//
+//   out[x] = alpha * a[x] + beta * c[x] + gamma * sum_{q in pass} P_q(x) * s_q(x) * in[x ^ bit_q]
+//
+// A CTA owns one tile: the 2^13 amplitudes whose index bits [0,L) and [H0,H0+M) vary
+// (L + M = 13; 64 KiB of shared memory, two CTAs per SM).
+//
+// Fast kernel (pass_kernel_v2), per thread (256 threads):
+//   * 32 amplitudes live in registers: local bit 0 (the two halves of a 16-byte load) and
+//     local bits 9..12 (16 rows `e`), so 5 of the 13 possible flips never leave the
+//     register file;
+//   * local bits 1..8 index the thread; their flips read the partner thread's pair with
+//     one LDS.128 from the staged tile;
+//   * the rule predicate P_q(x) comes from window lookup tables (a few KiB, L1-resident)
+//     instead of being recomputed per amplitude;
+//   * global traffic is 16-byte vector loads/stores, 128-byte rows at least.
+#pragma once
+#include "qca_common.cuh"
+
+namespace qca {
+
+constexpr int kPassThreads = 256;
+constexpr int kTile = 13;      // == kTileBits
+constexpr int kRegHigh = 4;    // local bits 9..12 are register rows
+constexpr int kRows = 1 << kRegHigh;
+constexpr int kRowShift = kTile - kRegHigh;  // 9
+
+struct PassArgs {
+    const double* in[2];     // vector the operator is applied to (plane 0/1)
+    const double* a_src[2];  // optional: + alpha * a_src[x]
+    const double* c_src[2];  // optional: + beta * c_src[x]   (may alias out)
+    double* out[2];
+    double alpha, beta, gamma;
+    unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
+    unsigned long long prefix;     // rank << local_bits: the sharded qubits of this rank
+    unsigned long long ntiles;
+    int low_bits, high_start, high_bits;  // tile = bits [0,low) U [high_start, high_start+high_bits)
+    int distance;
+    unsigned interval_mask;
+    // window tables (fast kernel): entry[w] = activity of the middle K bits of the (K+2d)-bit window w
+    const unsigned short* tab_lo;  // pass 0: K = 9-d, window = x bits [0,9) << d
+    const unsigned short* tab_hi;  // pass 0: K = 4+d, window = x bits [9-2d, 13+d); pass>=1: K = M, bits [H0-d, H0+M+d)
+};
+
+// ---------------------------------------------------------------------------
+// Generic kernel: any tile geometry, any distance <= 7.  Used for registers of fewer
+// than 13 qubits and for distance > 4; one amplitude at a time from shared memory.
+// ---------------------------------------------------------------------------
+template <typename I>
+__global__ void __launch_bounds__(kPassThreads) pass_kernel_generic(const PassArgs a) {
+    extern __shared__ double tile[];
+    const int plane = blockIdx.y;
+    const double* __restrict__ in = a.in[plane];
+    const double* __restrict__ asrc = a.a_src[plane];
+    const double* csrc = a.c_src[plane];
+    double* out = a.out[plane];
+    const int L = a.low_bits, H0 = a.high_start, M = a.high_bits;
+    const int T = L + M;
+    const unsigned tile_elems = 1u << T;
+    const unsigned low_mask = (1u << L) - 1u;
+    const int gap = H0 - L;
+
+    for (unsigned long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const I t_lo = (I)(t & ((1ull << gap) - 1ull));
+        const I t_hi = (I)(t >> gap);
+        const I base = (t_lo << L) | (t_hi << (H0 + M));
+        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            tile[y] = in[x];
+        }
+        __syncthreads();
+        for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            const I act = activity_word<I>(x | (I)a.prefix, a.distance, a.interval_mask) & (I)a.flip_mask;
+            double acc = 0.0;
+            for (int q = 0; q < T; ++q) {
+                const int g = q < L ? q : H0 + (q - L);
+                if ((act >> g) & 1) {
+                    const double v = tile[y ^ (1u << q)];
+                    acc += ((y >> q) & 1u) ? -v : v;  // K = sum_c P_c (sigma^-  -  sigma^+)_c
+                }
+            }
+            double r = a.gamma * acc;
+            if (asrc) r += a.alpha * asrc[x];
+            if (csrc) r += a.beta * csrc[x];
+            out[x] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fast kernel
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg_stream(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_rw(const double* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(double* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
+// FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
+template <typename I, int L, bool FLIP_LOW>
+__global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs a) {
+    constexpr int M = kTile - L;
+    constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
+    static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
+    extern __shared__ double tile[];
+    const int plane = blockIdx.y;
+    const double* __restrict__ in = a.in[plane];
+    const double* __restrict__ asrc = a.a_src[plane];
+    const double* csrc = a.c_src[plane];
+    double* out = a.out[plane];
+    const int H0 = a.high_start;
+    const int d = a.distance;
+    const unsigned tid = threadIdx.x;
+    constexpr unsigned low_mask = (1u << L) - 1u;
+
+    // tile base and this thread's part of the index
+    const unsigned long long t = blockIdx.x;
+    const int gap = H0 - L;
+    const I t_lo = (I)(t & ((1ull << gap) - 1ull));
+    const I t_hi = (I)(t >> gap);
+    const I base = (t_lo << L) | (t_hi << (H0 + M));
+    const unsigned y_thr = tid << 1;  // local bits 1..8
+    const I x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
+
+    // ---- stage the tile: 16 rows x one 16-byte pair per thread -------------------------------
+    double2 v[kRows];
+    auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
+        const unsigned ye = (unsigned)e << kRowShift;
+        return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
+    };
+#pragma unroll
+    for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + row_x(e));
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+#pragma unroll
+    for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
+
+    // ---- rule predicate words ------------------------------------------------------------------
+    // la[j] bit q: local bit q of element (e, j) is flipped by an active term
+    unsigned lo_act0 = 0, lo_act1 = 0;
+    if (FLIP_LOW) {
+        // bits [0, 9-d): window = x bits [0,9) shifted up by d (dead cells below the chain end)
+        const unsigned w = ((unsigned)x_thr & 0x1ffu) << d;
+        lo_act0 = a.tab_lo[w];
+        lo_act1 = a.tab_lo[w | (1u << d)];
+    }
+    // thread-bit signs: -1 where this thread's bit is set (sigma^- - sigma^+)
+    double sgn[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) sgn[b] = ((tid >> b) & 1u) ? -1.0 : 1.0;
+
+    __syncthreads();
+
+    const I pfx = (I)a.prefix;
+#pragma unroll
+    for (int e = 0; e < kRows; ++e) {
+        unsigned la0, la1;
+        if (FLIP_LOW) {
+            const int S = 9 - d;
+            const unsigned w = (unsigned)((row_x(e) | pfx) >> (9 - 2 * d)) & ((1u << (4 + 3 * d)) - 1u);
+            const unsigned hi_act = a.tab_hi[w];
+            la0 = lo_act0 | (hi_act << S);
+            la1 = lo_act1 | (hi_act << S);
+        } else {
+            const unsigned w = (unsigned)((row_x(e) | pfx) >> (H0 - d)) & ((1u << (M + 2 * d)) - 1u);
+            la0 = la1 = (unsigned)a.tab_hi[w] << L;
+        }
+        double acc0 = 0.0, acc1 = 0.0;
+        // local bit 0: the other half of the pair
+        if (QLO == 0) {
+            if (la0 & 1u) acc0 += v[e].y;
+            if (la1 & 1u) acc1 -= v[e].x;
+        }
+        // local bits 1..8: partner thread, same row
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b + 1 >= QLO) {
+                const double2 p = tile2[(e << (kRowShift - 1)) | (tid ^ (1u << b))];
+                if (la0 & (2u << b)) acc0 = fma(p.x, sgn[b], acc0);
+                if (la1 & (2u << b)) acc1 = fma(p.y, sgn[b], acc1);
+            }
+        }
+        // local bits 9..12: partner row, same thread (registers)
+#pragma unroll
+        for (int k = 0; k < kRegHigh; ++k) {
+            if (kRowShift + k >= QLO) {
+                const double2 p = v[e ^ (1 << k)];
+                if ((e >> k) & 1) {
+                    if (la0 & (1u << (kRowShift + k))) acc0 -= p.x;
+                    if (la1 & (1u << (kRowShift + k))) acc1 -= p.y;
+                } else {
+                    if (la0 & (1u << (kRowShift + k))) acc0 += p.x;
+                    if (la1 & (1u << (kRowShift + k))) acc1 += p.y;
+                }
+            }
+        }
+        double2 r;
+        r.x = a.gamma * acc0;
+        r.y = a.gamma * acc1;
+        if (asrc) {
+            const double2 s = ldg_stream(asrc + row_x(e));
+            r.x = fma(a.alpha, s.x, r.x);
+            r.y = fma(a.alpha, s.y, r.y);
+        }
+        if (csrc) {
+            const double2 s = ldg_rw(csrc + row_x(e));
+            r.x = fma(a.beta, s.x, r.x);
+            r.y = fma(a.beta, s.y, r.y);
+        }
+        stg_stream(out + row_x(e), r);
+    }
+}
+
+}  // namespace qca
