@@ -298,12 +298,13 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     a.tab_hi = e->d_tab_hi[pass_index];
     const int T = ps.low_bits + ps.high_bits;
     a.ntiles = e->namps >> T;
-    const int smem = (int)(sizeof(double) << T);
+    int smem = (int)(sizeof(double) << T);
     const bool wide = (e->rule.ncells > 31);
     void (*kern)(const PassArgs) = nullptr;
     if (e->fast_path && T == kTile)
         kern = wide ? select_fast_kernel<unsigned long long>(ps.low_bits) : select_fast_kernel<unsigned int>(ps.low_bits);
     const bool fast = kern != nullptr;
+    if (fast) smem = kPassSmemBytes;
     if (!fast) kern = wide ? pass_kernel_generic<unsigned long long> : pass_kernel_generic<unsigned int>;
     QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);

@@ -106,6 +106,23 @@ __device__ __forceinline__ void stg_stream(double* p, double2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Epilogue operands (a, c) are streamed through a per-thread ring of RING rows in shared memory,
+// filled by cp.async from kernel entry on: deep memory-level parallelism at no register cost.
+// pass 0 carries two operands (ring 4 + 4 rows), later passes one (ring 8): 32 KiB either way.
+constexpr int kRingRows0 = 4;
+constexpr int kRingRows1 = 8;
+constexpr int kPassSmemBytes = (8 << kTile) + 32768;
+
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
 template <typename I, int L, bool FLIP_LOW>
@@ -133,15 +150,25 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     const unsigned y_thr = tid << 1;  // local bits 1..8
     const I x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
 
-    // ---- stage the tile: 16 rows x one 16-byte pair per thread -------------------------------
-    double2 v[kRows];
+    constexpr int RING = FLIP_LOW ? kRingRows0 : kRingRows1;
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+    double2* ring_c = tile2 + (1 << (kTile - 1));          // [RING][256]
+    double2* ring_a = ring_c + RING * kPassThreads;        // [RING][256] (pass 0 only)
     auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
         const unsigned ye = (unsigned)e << kRowShift;
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
     };
+    // ---- start streaming the epilogue operands ------------------------------------------------
+#pragma unroll
+    for (int e = 0; e < RING; ++e) {
+        if (csrc) cp_async16(ring_c + e * kPassThreads + tid, csrc + row_x(e));
+        if (FLIP_LOW && asrc) cp_async16(ring_a + e * kPassThreads + tid, asrc + row_x(e));
+        cp_async_commit();
+    }
+    // ---- stage the tile: 16 rows x one 16-byte pair per thread -------------------------------
+    double2 v[kRows];
 #pragma unroll
     for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + row_x(e));
-    double2* tile2 = reinterpret_cast<double2*>(tile);
 #pragma unroll
     for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
 
@@ -207,17 +234,29 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         double2 r;
         r.x = a.gamma * acc0;
         r.y = a.gamma * acc1;
-        if (asrc) {
+        cp_async_wait<RING - 1>();  // the group of row e has landed (own data: no barrier needed)
+        if (FLIP_LOW) {
+            if (asrc) {
+                const double2 s = ring_a[(e % RING) * kPassThreads + tid];
+                r.x = fma(a.alpha, s.x, r.x);
+                r.y = fma(a.alpha, s.y, r.y);
+            }
+        } else if (asrc) {  // not used by the stepper (later passes carry only c), kept for generality
             const double2 s = ldg_stream(asrc + row_x(e));
             r.x = fma(a.alpha, s.x, r.x);
             r.y = fma(a.alpha, s.y, r.y);
         }
         if (csrc) {
-            const double2 s = ldg_rw(csrc + row_x(e));
+            const double2 s = ring_c[(e % RING) * kPassThreads + tid];
             r.x = fma(a.beta, s.x, r.x);
             r.y = fma(a.beta, s.y, r.y);
         }
         stg_stream(out + row_x(e), r);
+        if (e + RING < kRows) {  // refill the slot just consumed
+            if (csrc) cp_async16(ring_c + (e % RING) * kPassThreads + tid, csrc + row_x(e + RING));
+            if (FLIP_LOW && asrc) cp_async16(ring_a + (e % RING) * kPassThreads + tid, asrc + row_x(e + RING));
+        }
+        cp_async_commit();
     }
 }
 
