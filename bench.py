@@ -159,19 +159,20 @@ def b200_arm(args) -> None:
     import numpy as np
     import torch
     import qca_b200
-    from qca_b200 import _lib
+    from qca_b200 import _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} must be launched with torch.distributed.run, one rank per GPU "
+                         f"(WORLD_SIZE is {world})")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the B200 arm")
-    if world > 1:
-        raise SystemExit("multi-GPU sharding of the exact path is not wired up in this build")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a real (non-default) stream: handle 0 would make the library create its own stream and the
     # torch events below would not see the kernels
     torch.cuda.set_stream(torch.cuda.Stream())
@@ -182,42 +183,57 @@ def b200_arm(args) -> None:
     plist = qca_b200.states.plist(args.initial_state, rules)
     flags = _lib.QCA_FLAG_FORCE_COMPLEX if args.force_complex else 0
 
+    def make_engine(extra_flags=0):
+        if world > 1:
+            return sharding.ShardedExactEngine(rules, device=local_rank, flags=flags | extra_flags, stream=stream)
+        return _lib.ExactEngine(rules, device=local_rank, flags=flags | extra_flags, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        return max(sharding.gather_objects(float(x)))
+
     def one_step(engine):
-        engine.measure()          # Algorithm.measure: D2H of 4*N partial sums
+        engine.measure()          # Algorithm.measure: D2H of 4*N sums (+ host gather when sharded)
         engine.step(args.step_size, 1)
 
     # ---- device-resident throughput -------------------------------------------------------
-    eng = _lib.ExactEngine(rules, device=local_rank, flags=flags, stream=stream)
+    eng = make_engine()
     eng.set_product_state(plist)
     for _ in range(args.warmup):
         one_step(eng)
-    torch.cuda.synchronize()
+    barrier()
     eng.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record()
     for _ in range(args.steps):
         one_step(eng)
     ev1.record()
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     st = eng.stats()
     norm2 = eng.norm2()
     planes = st["planes"]
     value = args.steps / (ms * 1e-3)
     whole_step_gbs = st["pass_bytes"] / (ms * 1e-3) / 1e9
+    nvlink_gbs = st["remote_bytes"] / (ms * 1e-3) / 1e9
     eng.close()
 
     # ---- per-launch duration of the dominant kernel (event pair around every launch) ---------
-    prof = _lib.ExactEngine(rules, device=local_rank, flags=flags | _lib.QCA_FLAG_PROFILE, stream=stream)
+    prof = make_engine(_lib.QCA_FLAG_PROFILE)
     prof.set_product_state(plist)
     prof.step(args.step_size, 1)
-    torch.cuda.synchronize()
+    barrier()
     prof.reset_stats()
     prof.step(args.step_size, 1)
+    barrier()
     pst = prof.stats()
     prof.close()
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -229,62 +245,72 @@ def b200_arm(args) -> None:
     avg_ms = pst["profiled_pass_ms"] / max(pst["profiled_pass_launches"], 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "qca::pass_kernel (tile pass of the rule operator + fused Clenshaw update)",
+                "traffic": None, "kernel": "qca::pass_kernel_v2 (tile pass of the rule operator + fused Clenshaw update)",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": pst["pass_launches"],
-                "peak_source": peak_src, "whole_step_gbs": whole_step_gbs,
-                "note": "achieved = operand vectors read/written once per launch / CUDA-event launch duration; "
-                        "whole_step_gbs = same bytes / the timed region including measurement kernels"}
+                "peak_source": peak_src, "whole_step_gbs": whole_step_gbs, "per_gpu": True,
+                "nvlink_read_gbs_per_gpu": nvlink_gbs,
+                "note": "per GPU (rank 0): achieved = local operand vectors read/written once per launch / CUDA-event "
+                        "launch duration; whole_step_gbs = same bytes / the timed region including measurement; "
+                        "partner-rank reads over NVLink are not counted in achieved"}
 
     # ---- end to end through host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        namps = 1 << args.num_cells
+        namps = (1 << args.num_cells) // world
         host = torch.empty(2 * namps, dtype=torch.float64)
         try:
             host = host.pin_memory()
             pinned = True
         except Exception:
             pinned = False
-        e = _lib.ExactEngine(rules, device=local_rank, flags=flags, stream=stream)
+        e = make_engine()
         e.set_product_state(plist)
-        e.get_state_ptr(host.data_ptr(), namps)
+        raw = e._eng if world > 1 else e          # this rank's slice moves through the C ABI
+        raw.get_state_ptr(host.data_ptr(), namps)
 
         def e2e_step():
-            e.set_state_ptr(host.data_ptr(), namps)   # Exact.psi setter: H2D of complex128 psi
-            pop = e.measure()[0]                      # Algorithm.measure: D2H of the sums
-            e.step(args.step_size, 1)                 # Exact.do_time_step
-            e.get_state_ptr(host.data_ptr(), namps)   # Exact.psi getter: D2H of complex128 psi
+            raw.set_state_ptr(host.data_ptr(), namps)   # Exact.psi setter: H2D of this rank's complex128 slice
+            if world > 1:
+                e._resolve()
+            pop = e.measure()[0]                        # Algorithm.measure: D2H of the sums
+            e.step(args.step_size, 1)                   # Exact.do_time_step
+            raw.get_state_ptr(host.data_ptr(), namps)   # Exact.psi getter: D2H of the slice
             return pop
 
         e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(args.steps):
             e2e_step()
         a1.record()
-        torch.cuda.synchronize()
+        barrier()
         wall = time.perf_counter() - t0
-        e2e_ms = max(a0.elapsed_time(a1), wall * 1e3)
-        e2e = {"value": args.steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 16 * namps,
-               "d2h_bytes_per_step": 16 * namps + 8 * 4 * args.num_cells, "ms_per_step": e2e_ms / args.steps,
+        e2e_ms = max_over_ranks(max(a0.elapsed_time(a1), wall * 1e3))
+        e2e = {"value": args.steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 16 * namps * world,
+               "d2h_bytes_per_step": (16 * namps + 8 * 4 * args.num_cells) * world, "ms_per_step": e2e_ms / args.steps,
                "pinned": pinned,
-               "api": "ExactEngine.set_state(host psi) -> measure -> step -> get_state(host psi) over the C ABI"}
+               "api": "ExactEngine.set_state(host psi) -> measure -> step -> get_state(host psi) over the C ABI, "
+                      "every rank moving its own slice"}
         e.close()
         del host
 
-    cpu = None if args.no_cpu_baseline else cpu_reference_run(args, 200, 5)
+    cpu = None if (args.no_cpu_baseline or world > 1 or rank != 0) else cpu_reference_run(args, 200, 5)
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, planes, {"chebyshev_terms": st["last_terms"],
                                                      "passes_per_term": st["passes_per_apply"],
-                                                     "spectral_bound": st["spectral_bound"], "norm2_after": norm2}),
+                                                     "spectral_bound": st["spectral_bound"], "norm2_after": norm2,
+                                                     "sharding": f"top {world.bit_length() - 1} qubits over {world} ranks, "
+                                                                 "partner reads over NVLink peer memory" if world > 1 else "none"}),
             "roofline": roofline, "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": e2e, "gpu_launches": int(st["kernel_launches"]), "clocks": clocks}
+            "e2e": e2e, "gpu_launches": int(st["kernel_launches"]) * world, "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

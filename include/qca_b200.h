@@ -75,6 +75,19 @@ typedef struct qca_pass {
  * written to passes[0..capacity). */
 int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity, int32_t* npasses);
 
+/* A rule term that flips a qubit held by another rank (sharded register): this rank adds
+ * sign * [mask bit v set] * partner_vector[x] where v = top `distance` local bits of x. */
+typedef struct qca_remote_op {
+    int32_t pass;    /* tile pass whose epilogue carries the term */
+    int32_t partner; /* rank whose vector is read over NVLink */
+    int32_t qubit;   /* index bit of the flipped qubit (>= local_bits) */
+    int32_t sign;    /* +1 if this rank holds the qubit dead, -1 if alive */
+    uint32_t mask;   /* activity of the term per value of the top `distance` local bits */
+    int32_t shift;   /* local_bits - min(distance, local_bits) */
+} qca_remote_op_t;
+int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_op_t* ops,
+                        int32_t capacity, int32_t* nops);
+
 /* ------------------------------------------------------------------------
  * Exact evolution engine == algorithms/exact.py:9-27 (class Exact).
  * ---------------------------------------------------------------------- */
@@ -101,6 +114,11 @@ int32_t qca_exact_set_state(qca_exact_t h, const double* psi, uint64_t namps);
 /* MPS.from_density_distribution (mps.py:35-52) + as_vector, evaluated on the
  * device: amplitude of cell i is (sqrt(1-p_i), sqrt(p_i)). */
 int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_t ncells);
+/* Sharded engines only: whether the rotated state of this rank has non-zero real / imaginary
+ * parts, and the collective decision (logical OR over ranks) of how many planes to keep.  A
+ * sharded engine must be resolved after every set_state / set_product_state. */
+int32_t qca_exact_plane_flags(qca_exact_t h, int32_t* has_re, int32_t* has_im);
+int32_t qca_exact_resolve_planes(qca_exact_t h, int32_t has_re, int32_t has_im);
 /* Exact.psi getter, vector part (exact.py:19-20). */
 int32_t qca_exact_get_state(qca_exact_t h, double* psi, uint64_t namps);
 
@@ -140,6 +158,7 @@ typedef struct qca_exact_stats {
     double profiled_pass_ms;     /* sum of event-timed pass durations (QCA_FLAG_PROFILE) */
     uint64_t profiled_pass_launches;
     double device_bytes;         /* bytes of device memory held */
+    double remote_bytes;         /* bytes read from partner ranks over NVLink by pass launches */
 } qca_exact_stats_t;
 int32_t qca_exact_get_stats(qca_exact_t h, qca_exact_stats_t* out);
 int32_t qca_exact_reset_stats(qca_exact_t h);

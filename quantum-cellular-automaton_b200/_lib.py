@@ -41,11 +41,16 @@ class PassStruct(C.Structure):
                 ("reserved", C.c_int32), ("flip_mask", C.c_uint64)]
 
 
+class RemoteOpStruct(C.Structure):
+    _fields_ = [("pass_", C.c_int32), ("partner", C.c_int32), ("qubit", C.c_int32), ("sign", C.c_int32),
+                ("mask", C.c_uint32), ("shift", C.c_int32)]
+
+
 class ExactStats(C.Structure):
     _fields_ = [("spectral_bound", C.c_double), ("planes", C.c_int32), ("passes_per_apply", C.c_int32),
                 ("last_terms", C.c_int32), ("local_bits", C.c_int32), ("kernel_launches", C.c_uint64),
                 ("pass_launches", C.c_uint64), ("pass_bytes", C.c_double), ("profiled_pass_ms", C.c_double),
-                ("profiled_pass_launches", C.c_uint64), ("device_bytes", C.c_double)]
+                ("profiled_pass_launches", C.c_uint64), ("device_bytes", C.c_double), ("remote_bytes", C.c_double)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -61,6 +66,10 @@ SYMBOLS = {
     "qca_spectral_bound": (C.c_int32, [C.POINTER(RuleStruct), _dp]),
     "qca_chebyshev_plan": (C.c_int32, [C.c_double, C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_passes": (C.c_int32, [C.c_int32, C.POINTER(PassStruct), C.c_int32, C.POINTER(C.c_int32)]),
+    "qca_plan_remote": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.c_int32, C.POINTER(RemoteOpStruct), C.c_int32,
+                                    C.POINTER(C.c_int32)]),
+    "qca_exact_plane_flags": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "qca_exact_resolve_planes": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "qca_exact_create": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(RuleStruct), C.c_int32, C.c_int32,
                                      C.c_int32, C.c_uint32, C.c_void_p]),
     "qca_exact_destroy": (C.c_int32, [C.c_void_p]),
@@ -142,6 +151,16 @@ def plan_passes(local_bits: int) -> list[dict]:
             for p in buf]
 
 
+def plan_remote(rules, world_size: int, rank: int) -> list[dict]:
+    n = C.c_int32()
+    rs = rule_struct(rules)
+    check(lib.qca_plan_remote(C.byref(rs), world_size, rank, None, 0, C.byref(n)))
+    buf = (RemoteOpStruct * max(n.value, 1))()
+    check(lib.qca_plan_remote(C.byref(rs), world_size, rank, buf, max(n.value, 1), C.byref(n)))
+    return [dict(pass_index=o.pass_, partner=o.partner, qubit=o.qubit, sign=o.sign, mask=o.mask, shift=o.shift)
+            for o in buf[:n.value]]
+
+
 def measure_finish(sums: np.ndarray, ncells: int):
     sums = np.ascontiguousarray(sums, dtype=np.float64)
     pop, dpop, ent = np.empty(ncells), np.empty(ncells), np.empty(ncells)
@@ -165,6 +184,28 @@ class ExactEngine:
         check(lib.qca_exact_create(C.byref(self._h), C.byref(rs), device, world_size, rank, flags,
                                    C.c_void_p(stream) if stream else None))
         self.local_amps = int(lib.qca_exact_local_amps(self._h))
+
+    # -- sharding -----------------------------------------------------------------------------
+    def ipc_handles(self) -> np.ndarray:
+        """This rank's exported buffers, uint8[count, 64] (empty when not sharded)."""
+        count = lib.qca_exact_ipc_count(self._h)
+        out = np.zeros((count, QCA_IPC_HANDLE_BYTES), dtype=np.uint8)
+        for i in range(count):
+            check(lib.qca_exact_ipc_export(self._h, i, C.c_void_p(out[i].ctypes.data)))
+        return out
+
+    def ipc_import(self, table: np.ndarray) -> None:
+        """table: uint8[world, count, 64] gathered from all ranks."""
+        table = np.ascontiguousarray(table, dtype=np.uint8)
+        check(lib.qca_exact_ipc_import(self._h, C.c_void_p(table.ctypes.data), table.shape[0], table.shape[1]))
+
+    def plane_flags(self) -> tuple[bool, bool]:
+        re, im = C.c_int32(), C.c_int32()
+        check(lib.qca_exact_plane_flags(self._h, C.byref(re), C.byref(im)))
+        return bool(re.value), bool(im.value)
+
+    def resolve_planes(self, has_re: bool, has_im: bool) -> None:
+        check(lib.qca_exact_resolve_planes(self._h, int(has_re), int(has_im)))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:

@@ -10,14 +10,18 @@ from __future__ import annotations
 import numpy as np
 
 from .algorithm import Algorithm
-from .. import _lib
+from .. import _lib, sharding
 from ..tensor_networks import MPS, MPO
 
 
 class Exact(Algorithm):
 
     def __init__(self, psi_0: MPS, H: MPO, args, *, device: int = 0, stream: int | None = None,
-                 force_complex: bool = False, profile: bool = False) -> None:
+                 force_complex: bool = False, profile: bool = False, group=None) -> None:
+        """Extra keyword arguments (all optional): CUDA `device` index, `stream` handle to launch
+        on, `force_complex` to keep both real planes, `profile` for per-launch event timing, and a
+        torch.distributed `group`: when torch.distributed is initialised with more than one rank
+        the register is sharded over the ranks (one process per GPU)."""
         rules = args.rules
         if H is not None:
             expected = MPO.hamiltonian_from_rules(rules)
@@ -27,7 +31,10 @@ class Exact(Algorithm):
                     "Exact evaluates the rule Hamiltonian MPO.hamiltonian_from_rules(args.rules) "
                     "matrix-free; the MPO passed in is a different operator")
         flags = (_lib.QCA_FLAG_FORCE_COMPLEX if force_complex else 0) | (_lib.QCA_FLAG_PROFILE if profile else 0)
-        self._engine = _lib.ExactEngine(rules, device=device, flags=flags, stream=stream)
+        if sharding.world_and_rank(group)[0] > 1:
+            self._engine = sharding.ShardedExactEngine(rules, device=device, flags=flags, stream=stream, group=group)
+        else:
+            self._engine = _lib.ExactEngine(rules, device=device, flags=flags, stream=stream)
         super().__init__(psi_0, H, args)
 
     # -- Algorithm interface --------------------------------------------------------------

@@ -181,8 +181,41 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 }
 
 // ---------------------------------------------------------------------------
+// Cross-GPU barrier over peer-mapped flags (one process per GPU, no NCCL on the data path):
+// thread r publishes `epoch` into rank r's flag slot for this rank, then waits until rank r
+// has published the same epoch here.  Stream order makes every earlier kernel of this rank
+// complete (and visible at system scope) before the flags are written.
+// ---------------------------------------------------------------------------
+struct BarrierArgs {
+    unsigned long long* flags[8];  // flags[r]: rank r's flag array (peer mapped), 8 slots
+    int world, rank;
+    unsigned long long epoch;
+};
+
+__global__ void barrier_kernel(const BarrierArgs b) {
+    const int r = threadIdx.x;
+    if (r >= b.world || r == b.rank) return;
+    __threadfence_system();
+    volatile unsigned long long* theirs = b.flags[r] + b.rank;
+    *theirs = b.epoch;
+    __threadfence_system();
+    volatile unsigned long long* mine = b.flags[b.rank] + r;
+    const long long t0 = clock64();
+    while (*mine < b.epoch) {
+        if (clock64() - t0 > 60000000000ll) {  // ~30 s: a peer died; fail instead of hanging the box
+            printf("qca_b200: barrier timeout on rank %d waiting for rank %d (epoch %llu)\n", b.rank, r, b.epoch);
+            __trap();
+        }
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------
+constexpr int kMaxWorld = 8;
+constexpr int kIpcBuffers = 7;  // 3 vectors x 2 planes + barrier flags
+
 struct Engine {
     qca_rule_t rule{};
     int device = 0, world = 1, rank = 0, rank_bits = 0, local_bits = 0;
@@ -193,9 +226,11 @@ struct Engine {
     double* plane[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     int cur = 0;          // vector index of the resident state
     int nplanes = 0;      // 0: no state yet
+    bool resolved = true; // sharded: planes agreed with the other ranks
     int g_quarter = 0;    // psi = i^g_quarter * D * phi
     double bound = 0.0;   // spectral bound R
     std::vector<qca_pass_t> passes;
+    std::vector<qca_remote_op_t> remote;
     double2* staging = nullptr;
     unsigned long long staging_amps = 0;
     unsigned long long* d_maxabs = nullptr;
@@ -204,12 +239,18 @@ struct Engine {
     double* d_amp = nullptr;
     int measure_blocks = 0;
     int num_sms = 148;
-    // stats
-    qca_exact_stats_t st{};
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
     // window lookup tables of the fast pass kernel (device), one pair per pass
     std::vector<unsigned short*> d_tab_lo, d_tab_hi;
     bool fast_path = false;
+    // sharding
+    unsigned long long* d_flags = nullptr;
+    double* peer_plane[kMaxWorld][3][2] = {};
+    unsigned long long* peer_flags[kMaxWorld] = {};
+    bool peers_ready = false;
+    unsigned long long epoch = 0;
+    // stats
+    qca_exact_stats_t st{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
 
     size_t plane_bytes() const { return (size_t)namps * sizeof(double); }
 };
@@ -227,7 +268,7 @@ static int32_t ensure_plane(Engine* e, int v, int p) {
 }
 
 static void release_plane(Engine* e, int v, int p) {
-    if (!e->plane[v][p]) return;
+    if (!e->plane[v][p] || e->world > 1) return;  // sharded planes are exported: never freed
     cudaFree(e->plane[v][p]);
     e->plane[v][p] = nullptr;
     e->st.device_bytes -= (double)e->plane_bytes();
@@ -250,10 +291,11 @@ static int32_t upload_table(Engine* e, const std::vector<unsigned short>& tab, u
     return QCA_OK;
 }
 
-// The fast kernel needs full 13-bit tiles and window tables of sane size (distance <= 4).
+// The fast kernel needs full 13-bit tiles, window tables of sane size (distance <= 4) and, when
+// sharded, a later pass to carry the remote terms.
 static int32_t build_tables(Engine* e) {
     const int d = e->rule.distance;
-    e->fast_path = (e->local_bits >= kTile) && d <= 4;
+    e->fast_path = (e->local_bits >= kTile) && d <= 4 && (e->world == 1 || e->passes.size() >= 2);
     e->d_tab_lo.assign(e->passes.size(), nullptr);
     e->d_tab_hi.assign(e->passes.size(), nullptr);
     if (!e->fast_path) return QCA_OK;
@@ -270,21 +312,16 @@ static int32_t build_tables(Engine* e) {
     return QCA_OK;
 }
 
-template <typename I>
-static void (*select_fast_kernel(int L))(const PassArgs) {
-    switch (L) {
-        case 13: return pass_kernel_v2<I, 13, true>;
-        case 12: return pass_kernel_v2<I, 12, false>;
-        case 11: return pass_kernel_v2<I, 11, false>;
-        case 10: return pass_kernel_v2<I, 10, false>;
-        case 9: return pass_kernel_v2<I, 9, false>;
-        case 8: return pass_kernel_v2<I, 8, false>;
-        case 7: return pass_kernel_v2<I, 7, false>;
-        case 6: return pass_kernel_v2<I, 6, false>;
-        case 5: return pass_kernel_v2<I, 5, false>;
-        case 4: return pass_kernel_v2<I, 4, false>;
-        default: return nullptr;
-    }
+static int32_t launch_barrier(Engine* e) {
+    if (e->world == 1) return QCA_OK;
+    QCA_REQUIRE(e->peers_ready, QCA_ERR_STATE, "sharded engine used before qca_exact_ipc_import");
+    BarrierArgs b{};
+    for (int r = 0; r < e->world; ++r) b.flags[r] = e->peer_flags[r];
+    b.world = e->world; b.rank = e->rank; b.epoch = ++e->epoch;
+    barrier_kernel<<<1, 32, 0, e->stream>>>(b);
+    QCA_CUDA(cudaGetLastError());
+    e->st.kernel_launches += 1;
+    return QCA_OK;
 }
 
 static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
@@ -300,12 +337,12 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     a.ntiles = e->namps >> T;
     int smem = (int)(sizeof(double) << T);
     const bool wide = (e->rule.ncells > 31);
-    void (*kern)(const PassArgs) = nullptr;
+    PassKernel kern = nullptr;
     if (e->fast_path && T == kTile)
-        kern = wide ? select_fast_kernel<unsigned long long>(ps.low_bits) : select_fast_kernel<unsigned int>(ps.low_bits);
+        kern = wide ? fast_pass_kernel_u64(ps.low_bits, a.nstreams) : fast_pass_kernel_u32(ps.low_bits, a.nstreams);
     const bool fast = kern != nullptr;
     if (fast) smem = kPassSmemBytes;
-    if (!fast) kern = wide ? pass_kernel_generic<unsigned long long> : pass_kernel_generic<unsigned int>;
+    else kern = generic_pass_kernel(wide);
     QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
     dim3 grid(gx, e->nplanes, 1);
@@ -321,34 +358,49 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
         QCA_CUDA(cudaEventRecord(ev1, e->stream));
         e->prof.emplace_back(ev0, ev1);
     }
-    // algorithmic bytes: every operand vector once per plane
+    // algorithmic bytes: every LOCAL operand vector once per plane (remote operands travel over
+    // NVLink and are accounted separately)
     double vecs = 2.0;  // in + out
-    if (a.a_src[0]) vecs += 1.0;
-    if (a.c_src[0]) vecs += 1.0;
+    double remote = 0.0;
+    for (int k = 0; k < a.nstreams; ++k) {
+        if (a.s[k].bit < 0) vecs += 1.0;
+        else remote += (double)__builtin_popcount(a.s[k].mask) / (double)(1u << std::min(e->rule.distance, e->local_bits));
+    }
     e->st.pass_bytes += vecs * (double)e->plane_bytes() * e->nplanes;
+    e->st.remote_bytes += remote * (double)e->plane_bytes() * e->nplanes;
     e->st.pass_launches += 1;
     e->st.kernel_launches += 1;
     return QCA_OK;
 }
 
-// out = alpha*a + beta*c + gamma * K in      (a, c optional; c may be out)
+// out = alpha*a + beta*c + gamma * K in      (a, c optional; c may be out).  Sharded: `in` must be
+// complete on every rank (barrier) because remote terms read the partner's copy of it.
 static int32_t apply_operator(Engine* e, int v_out, int v_in, int v_a, double alpha, int v_c, double beta,
                               double gamma) {
+    QCA_CHECK(launch_barrier(e));
     for (size_t i = 0; i < e->passes.size(); ++i) {
         PassArgs a{};
-        for (int p = 0; p < 2; ++p) {
-            a.in[p] = e->plane[v_in][p];
-            a.out[p] = e->plane[v_out][p];
-            if (i == 0) {
-                a.a_src[p] = v_a >= 0 ? e->plane[v_a][p] : nullptr;
-                a.c_src[p] = v_c >= 0 ? e->plane[v_c][p] : nullptr;
-            } else {
-                a.a_src[p] = nullptr;
-                a.c_src[p] = e->plane[v_out][p];
-            }
+        int ns = 0;
+        auto add_local = [&](int v, double coef) {
+            EpiStream& st = a.s[ns++];
+            for (int p = 0; p < 2; ++p) st.ptr[p] = e->plane[v][p];
+            st.coef = coef; st.mask = ~0u; st.shift = 0; st.bit = -1;
+        };
+        for (int p = 0; p < 2; ++p) { a.in[p] = e->plane[v_in][p]; a.out[p] = e->plane[v_out][p]; }
+        if (i == 0) {
+            if (v_a >= 0) add_local(v_a, alpha);
+            if (v_c >= 0) add_local(v_c, beta);
+        } else {
+            add_local(v_out, 1.0);
         }
-        a.alpha = (i == 0) ? alpha : 0.0;
-        a.beta = (i == 0) ? beta : 1.0;
+        for (const qca_remote_op_t& op : e->remote) {
+            if (op.pass != (int)i) continue;
+            QCA_REQUIRE(ns < kMaxStreams, QCA_ERR_UNSUPPORTED, "too many remote terms in one pass");
+            EpiStream& st = a.s[ns++];
+            for (int p = 0; p < 2; ++p) st.ptr[p] = e->peer_plane[op.partner][v_in][p];
+            st.coef = gamma * (double)op.sign; st.mask = op.mask; st.shift = op.shift; st.bit = op.qubit;
+        }
+        a.nstreams = ns;
         a.gamma = gamma;
         QCA_CHECK(launch_pass(e, i, a));
     }
@@ -387,6 +439,9 @@ static int32_t step_once(Engine* e, double step_size) {
     const int P = e->cur;
     int X = (P + 1) % 3, Y = (P + 2) % 3;
     const double R = e->bound;
+    // (sharded: the barrier that opens the first apply also orders this write after every
+    //  partner's remote reads of X in the previous step)
+    QCA_CHECK(launch_barrier(e));
     QCA_CHECK(launch_scale(e, X, P, a[K]));  // B_K
     for (int k = K - 1; k >= 1; --k) {
         const bool first = (k == K - 1);  // B_{K+1} = 0
@@ -412,32 +467,49 @@ static int32_t finish_profile(Engine* e) {
     return QCA_OK;
 }
 
-// After a state upload: decide the number of planes from the exact maxima.
-static int32_t settle_planes(Engine* e) {
+static int32_t read_plane_flags(Engine* e, bool* has_re, bool* has_im) {
     unsigned long long h[2];
     QCA_CUDA(cudaMemcpyAsync(h, e->d_maxabs, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
     QCA_CUDA(cudaStreamSynchronize(e->stream));
-    const bool has_re = h[0] != 0, has_im = h[1] != 0;
+    *has_re = h[0] != 0; *has_im = h[1] != 0;
+    return QCA_OK;
+}
+
+// Decide the number of planes from the exact maxima (of all ranks when sharded).
+static int32_t settle_planes(Engine* e, bool has_re, bool has_im) {
     e->g_quarter = 0;
-    if (e->world > 1 || (e->flags & QCA_FLAG_FORCE_COMPLEX) || (has_re && has_im)) {
+    if ((e->flags & QCA_FLAG_FORCE_COMPLEX) || (has_re && has_im)) {
         e->nplanes = 2;
     } else if (has_im) {  // purely imaginary rotated state: psi = i * D * (im plane)
         std::swap(e->plane[e->cur][0], e->plane[e->cur][1]);
+        // every rank takes the same decision, so the views of the partners' planes swap too
+        for (int r = 0; r < e->world && e->world > 1; ++r) std::swap(e->peer_plane[r][e->cur][0], e->peer_plane[r][e->cur][1]);
         e->g_quarter = 1;
         e->nplanes = 1;
     } else {
         e->nplanes = 1;
     }
     if (e->nplanes == 1) release_plane(e, e->cur, 1);
+    e->resolved = true;
     return QCA_OK;
 }
 
 static int32_t prepare_upload(Engine* e) {
-    // keep only the state vector's planes while uploading; work planes come back lazily
     QCA_CHECK(ensure_plane(e, e->cur, 0));
     QCA_CHECK(ensure_plane(e, e->cur, 1));
     QCA_CUDA(cudaMemsetAsync(e->d_maxabs, 0, 2 * sizeof(unsigned long long), e->stream));
     return QCA_OK;
+}
+
+static int32_t finish_upload(Engine* e) {
+    if (e->world > 1) {  // the ranks must agree: qca_exact_resolve_planes
+        e->nplanes = 2;
+        e->resolved = false;
+        return QCA_OK;
+    }
+    bool re, im;
+    QCA_CHECK(read_plane_flags(e, &re, &im));
+    return settle_planes(e, re, im);
 }
 
 static int32_t ensure_staging(Engine* e) {
@@ -465,12 +537,12 @@ static int32_t upload_vector(Engine* e, int v, const double* host, bool track) {
     return QCA_OK;
 }
 
-static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter) {
+static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter, bool both_planes) {
     QCA_CHECK(ensure_staging(e));
     for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
         const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
         pack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
-            e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->prefix, extra_quarter);
+            e->staging, e->plane[v][0], both_planes ? e->plane[v][1] : nullptr, off, cnt, e->prefix, extra_quarter);
         QCA_CUDA(cudaGetLastError());
         e->st.kernel_launches += 1;
         QCA_CUDA(cudaMemcpyAsync(host + 2 * off, e->staging, cnt * sizeof(double2), cudaMemcpyDeviceToHost, e->stream));
@@ -481,16 +553,34 @@ static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter
 }
 
 static int32_t measure_partial(Engine* e, double* sums) {
-    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "measure before a state was set");
+    QCA_REQUIRE(e->nplanes > 0 && e->resolved, QCA_ERR_STATE, "measure before a state was set (and resolved)");
     const int n = e->rule.ncells;
     const double* re = e->plane[e->cur][0];
     const double* im = e->nplanes == 2 ? e->plane[e->cur][1] : nullptr;
+    QCA_CHECK(launch_barrier(e));  // sharded: partner states are final before they are read
     QCA_CUDA(cudaMemsetAsync(e->d_sums, 0, 4 * n * sizeof(double), e->stream));
+    auto blocks_for = [&](unsigned long long npairs) {
+        return (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + kMeasureThreads - 1) / kMeasureThreads, (unsigned long long)e->measure_blocks));
+    };
     for (int bit = 0; bit < e->local_bits; ++bit) {
         const int cell = n - 1 - bit;
         const unsigned long long npairs = e->namps >> 1;
-        const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + kMeasureThreads - 1) / kMeasureThreads, (unsigned long long)e->measure_blocks));
+        const int blocks = blocks_for(npairs);
         measure_pairs_kernel<<<blocks, kMeasureThreads, 0, e->stream>>>(re, im, re, im, bit, npairs, e->d_partials);
+        QCA_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<1, 128, 0, e->stream>>>(e->d_partials, blocks, e->d_sums + 4 * cell);
+        QCA_CUDA(cudaGetLastError());
+        e->st.kernel_launches += 2;
+    }
+    // sharded qubits: the rank holding the qubit dead pairs its slice with the partner's
+    for (int j = 0; j < e->rank_bits; ++j) {
+        if ((e->rank >> j) & 1) continue;
+        const int cell = n - 1 - (e->local_bits + j);
+        const int partner = e->rank ^ (1 << j);
+        const double* pre = e->peer_plane[partner][e->cur][0];
+        const double* pim = e->nplanes == 2 ? e->peer_plane[partner][e->cur][1] : nullptr;
+        const int blocks = blocks_for(e->namps);
+        measure_pairs_kernel<<<blocks, kMeasureThreads, 0, e->stream>>>(re, im, pre, pim, -1, e->namps, e->d_partials);
         QCA_CUDA(cudaGetLastError());
         reduce_partials_kernel<<<1, 128, 0, e->stream>>>(e->d_partials, blocks, e->d_sums + 4 * cell);
         QCA_CUDA(cudaGetLastError());
@@ -528,7 +618,8 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     int rank_bits = 0;
     while ((1 << rank_bits) < world_size) ++rank_bits;
     QCA_REQUIRE(rule->ncells - rank_bits >= 1, QCA_ERR_ARG, "ncells %d too small for %d ranks", rule->ncells, world_size);
-    QCA_REQUIRE(world_size == 1, QCA_ERR_UNSUPPORTED, "multi-GPU sharding is not wired up yet");
+    QCA_REQUIRE(world_size == 1 || rule->ncells - rank_bits >= rule->distance, QCA_ERR_UNSUPPORTED,
+                "sharding needs at least `distance` local qubits");
     int ndev = 0;
     QCA_CUDA(cudaGetDeviceCount(&ndev));
     QCA_REQUIRE(device >= 0 && device < ndev, QCA_ERR_CUDA, "device %d not present (%d visible)", device, ndev);
@@ -548,6 +639,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     e->num_sms = prop.multiProcessorCount;
     e->bound = qca::spectral_bound(*rule);
     qca::plan_passes(e->local_bits, e->passes);
+    if (int32_t rc = qca::plan_remote(*rule, world_size, rank, e->remote)) { delete h; return rc; }
     e->st.spectral_bound = e->bound;
     e->st.passes_per_apply = (int32_t)e->passes.size();
     e->st.local_bits = e->local_bits;
@@ -559,12 +651,25 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
         e->own_stream = true;
     }
     e->measure_blocks = e->num_sms * 8;
-    if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
     bool ok = cudaMalloc(&e->d_maxabs, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&e->d_partials, 4ull * e->measure_blocks * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_sums, 4ull * rule->ncells * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
+    if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
+    if (world_size > 1) {
+        // every plane exists up front so that it can be exported once
+        for (int v = 0; v < 3; ++v)
+            for (int p = 0; p < 2; ++p) {
+                if (int32_t rc = qca::ensure_plane(e, v, p)) { qca_exact_destroy(h); return rc; }
+                e->peer_plane[rank][v][p] = e->plane[v][p];
+            }
+        if (cudaMalloc(&e->d_flags, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(e->d_flags, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+            qca::set_error("cudaMalloc of barrier flags failed"); qca_exact_destroy(h); return QCA_ERR_NOMEM;
+        }
+        e->peer_flags[rank] = e->d_flags;
+    }
     *out = h;
     return QCA_OK;
 }
@@ -575,9 +680,17 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& pr : e->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (e->peers_ready) {
+        for (int r = 0; r < e->world; ++r) {
+            if (r == e->rank) continue;
+            for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->peer_plane[r][v][p]) cudaIpcCloseMemHandle(e->peer_plane[r][v][p]);
+            if (e->peer_flags[r]) cudaIpcCloseMemHandle(e->peer_flags[r]);
+        }
+    }
     for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->plane[v][p]) cudaFree(e->plane[v][p]);
     for (auto* p : e->d_tab_lo) if (p) cudaFree(p);
     for (auto* p : e->d_tab_hi) if (p) cudaFree(p);
+    if (e->d_flags) cudaFree(e->d_flags);
     if (e->staging) cudaFree(e->staging);
     if (e->d_maxabs) cudaFree(e->d_maxabs);
     if (e->d_partials) cudaFree(e->d_partials);
@@ -598,7 +711,7 @@ int32_t qca_exact_set_state(qca_exact_t h, const double* psi, uint64_t namps) {
     QCA_CUDA(cudaSetDevice(e->device));
     QCA_CHECK(qca::prepare_upload(e));
     QCA_CHECK(qca::upload_vector(e, e->cur, psi, true));
-    return qca::settle_planes(e);
+    return qca::finish_upload(e);
 }
 
 int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_t ncells) {
@@ -619,23 +732,40 @@ int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_
     QCA_CUDA(cudaGetLastError());
     e->st.kernel_launches += 1;
     QCA_CUDA(cudaStreamSynchronize(e->stream));  // amp is a host temporary
-    return qca::settle_planes(e);
+    return qca::finish_upload(e);
+}
+
+int32_t qca_exact_plane_flags(qca_exact_t h, int32_t* has_re, int32_t* has_im) {
+    QCA_REQUIRE(h && has_re && has_im, QCA_ERR_ARG, "NULL argument");
+    QCA_REQUIRE(h->e.nplanes > 0, QCA_ERR_STATE, "no state uploaded");
+    QCA_CUDA(cudaSetDevice(h->e.device));
+    bool re, im;
+    QCA_CHECK(qca::read_plane_flags(&h->e, &re, &im));
+    *has_re = re; *has_im = im;
+    return QCA_OK;
+}
+
+int32_t qca_exact_resolve_planes(qca_exact_t h, int32_t has_re, int32_t has_im) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    QCA_REQUIRE(h->e.nplanes > 0, QCA_ERR_STATE, "no state uploaded");
+    QCA_CUDA(cudaSetDevice(h->e.device));
+    return qca::settle_planes(&h->e, has_re != 0, has_im != 0);
 }
 
 int32_t qca_exact_get_state(qca_exact_t h, double* psi, uint64_t namps) {
     QCA_REQUIRE(h && psi, QCA_ERR_ARG, "NULL argument");
     Engine* e = &h->e;
-    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "get_state before a state was set");
+    QCA_REQUIRE(e->nplanes > 0 && e->resolved, QCA_ERR_STATE, "get_state before a state was set (and resolved)");
     QCA_REQUIRE(namps == e->namps, QCA_ERR_ARG, "buffer has %llu amplitudes, engine holds %llu",
                 (unsigned long long)namps, e->namps);
     QCA_CUDA(cudaSetDevice(e->device));
-    return qca::download_vector(e, e->cur, psi, e->g_quarter);
+    return qca::download_vector(e, e->cur, psi, e->g_quarter, e->nplanes == 2);
 }
 
 int32_t qca_exact_step(qca_exact_t h, double step_size, int32_t nsteps) {
     QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
     Engine* e = &h->e;
-    QCA_REQUIRE(e->nplanes > 0, QCA_ERR_STATE, "step before a state was set");
+    QCA_REQUIRE(e->nplanes > 0 && e->resolved, QCA_ERR_STATE, "step before a state was set (and resolved)");
     QCA_REQUIRE(nsteps >= 0, QCA_ERR_ARG, "nsteps must be >= 0");
     QCA_REQUIRE(isfinite(step_size), QCA_ERR_ARG, "step_size must be finite");
     QCA_CUDA(cudaSetDevice(e->device));
@@ -695,7 +825,8 @@ int32_t qca_exact_apply_h(qca_exact_t h, const double* in, double* out, uint64_t
         if ((rc = qca::upload_vector(e, X, in, false))) break;
         // H psi = D (i K) D^-1 psi: apply K in the rotated frame, one extra quarter turn on the way out
         if ((rc = qca::apply_operator(e, Y, X, -1, 0.0, -1, 0.0, 1.0))) break;
-        rc = qca::download_vector(e, Y, out, 1);
+        if ((rc = qca::launch_barrier(e))) break;  // sharded: partners are done reading X
+        rc = qca::download_vector(e, Y, out, 1, true);
     } while (0);
     e->nplanes = saved_planes;
     if (saved_planes < 2) { qca::release_plane(e, X, 1); qca::release_plane(e, Y, 1); }
@@ -710,7 +841,6 @@ int32_t qca_exact_norm2(qca_exact_t h, double* norm2) {
     const double* re = e->plane[e->cur][0];
     const double* im = e->nplanes == 2 ? e->plane[e->cur][1] : nullptr;
     double hsum[4];
-    if (e->local_bits == 0) { *norm2 = 0; return QCA_OK; }
     const unsigned long long npairs = e->namps >> 1;
     const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + qca::kMeasureThreads - 1) / qca::kMeasureThreads, (unsigned long long)e->measure_blocks));
     qca::measure_pairs_kernel<<<blocks, qca::kMeasureThreads, 0, e->stream>>>(re, im, re, im, 0, npairs, e->d_partials);
@@ -738,21 +868,51 @@ int32_t qca_exact_reset_stats(qca_exact_t h) {
     QCA_CUDA(cudaSetDevice(h->e.device));
     QCA_CHECK(qca::finish_profile(&h->e));
     Engine* e = &h->e;
-    e->st.kernel_launches = 0; e->st.pass_launches = 0; e->st.pass_bytes = 0.0;
+    e->st.kernel_launches = 0; e->st.pass_launches = 0; e->st.pass_bytes = 0.0; e->st.remote_bytes = 0.0;
     e->st.profiled_pass_ms = 0.0; e->st.profiled_pass_launches = 0;
     return QCA_OK;
 }
 
-int32_t qca_exact_ipc_count(qca_exact_t h) { (void)h; return 0; }
-int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IPC_HANDLE_BYTES]) {
-    (void)h; (void)index; (void)handle;
-    qca::set_error("multi-GPU sharding is not wired up yet");
-    return QCA_ERR_UNSUPPORTED;
+// ---- sharding: CUDA IPC peer mapping ----------------------------------------------------------
+int32_t qca_exact_ipc_count(qca_exact_t h) { return (h && h->e.world > 1) ? qca::kIpcBuffers : 0; }
+
+static void* ipc_buffer(Engine* e, int index) {
+    return index < 6 ? (void*)e->plane[index / 2][index % 2] : (void*)e->d_flags;
 }
+
+int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IPC_HANDLE_BYTES]) {
+    QCA_REQUIRE(h && handle, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->world > 1, QCA_ERR_STATE, "engine is not sharded");
+    QCA_REQUIRE(index >= 0 && index < qca::kIpcBuffers, QCA_ERR_ARG, "buffer index %d out of range", index);
+    static_assert(sizeof(cudaIpcMemHandle_t) == QCA_IPC_HANDLE_BYTES, "handle size");
+    QCA_CUDA(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t mh;
+    QCA_CUDA(cudaIpcGetMemHandle(&mh, ipc_buffer(e, index)));
+    memcpy(handle, &mh, sizeof(mh));
+    return QCA_OK;
+}
+
 int32_t qca_exact_ipc_import(qca_exact_t h, const uint8_t* handles, int32_t world_size, int32_t count) {
-    (void)h; (void)handles; (void)world_size; (void)count;
-    qca::set_error("multi-GPU sharding is not wired up yet");
-    return QCA_ERR_UNSUPPORTED;
+    QCA_REQUIRE(h && handles, QCA_ERR_ARG, "NULL argument");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->world > 1 && world_size == e->world && count == qca::kIpcBuffers, QCA_ERR_ARG,
+                "handle table does not match the engine (world %d, count %d)", world_size, count);
+    QCA_REQUIRE(!e->peers_ready, QCA_ERR_STATE, "peers already imported");
+    QCA_CUDA(cudaSetDevice(e->device));
+    for (int r = 0; r < e->world; ++r) {
+        if (r == e->rank) continue;
+        for (int i = 0; i < count; ++i) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, handles + ((size_t)r * count + i) * QCA_IPC_HANDLE_BYTES, sizeof(mh));
+            void* ptr = nullptr;
+            QCA_CUDA(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+            if (i < 6) e->peer_plane[r][i / 2][i % 2] = (double*)ptr;
+            else e->peer_flags[r] = (unsigned long long*)ptr;
+        }
+    }
+    e->peers_ready = true;
+    return QCA_OK;
 }
 
 }  // extern "C"

@@ -25,12 +25,27 @@ constexpr int kRegHigh = 4;    // local bits 9..12 are register rows
 constexpr int kRows = 1 << kRegHigh;
 constexpr int kRowShift = kTile - kRegHigh;  // 9
 
+constexpr int kMaxStreams = 4;
+
+// One epilogue operand:  out[x] += coef * [active(x)] * ptr[x].
+// Local recurrence operands (a, c) are unconditional; a *remote* operand is the partner rank's
+// copy of `in` (peer memory over NVLink) for a term that flips a sharded qubit: it is active where
+// the rule predicate of that qubit holds, a function of the top `distance` local bits only.
+struct EpiStream {
+    const double* ptr[2];  // per plane
+    double coef;
+    unsigned mask;         // fast kernel: active iff (mask >> ((x >> shift) & 15)) & 1; ~0u = always
+    int shift;
+    int bit;               // generic kernel: active iff activity bit `bit` of x is set; -1 = always
+    int pad;
+};
+
 struct PassArgs {
-    const double* in[2];     // vector the operator is applied to (plane 0/1)
-    const double* a_src[2];  // optional: + alpha * a_src[x]
-    const double* c_src[2];  // optional: + beta * c_src[x]   (may alias out)
+    const double* in[2];   // vector the operator is applied to (plane 0/1)
     double* out[2];
-    double alpha, beta, gamma;
+    double gamma;
+    EpiStream s[kMaxStreams];
+    int nstreams;
     unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
     unsigned long long prefix;     // rank << local_bits: the sharded qubits of this rank
     unsigned long long ntiles;
@@ -51,8 +66,6 @@ __global__ void __launch_bounds__(kPassThreads) pass_kernel_generic(const PassAr
     extern __shared__ double tile[];
     const int plane = blockIdx.y;
     const double* __restrict__ in = a.in[plane];
-    const double* __restrict__ asrc = a.a_src[plane];
-    const double* csrc = a.c_src[plane];
     double* out = a.out[plane];
     const int L = a.low_bits, H0 = a.high_start, M = a.high_bits;
     const int T = L + M;
@@ -71,7 +84,9 @@ __global__ void __launch_bounds__(kPassThreads) pass_kernel_generic(const PassAr
         __syncthreads();
         for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
             const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
-            const I act = activity_word<I>(x | (I)a.prefix, a.distance, a.interval_mask) & (I)a.flip_mask;
+            const unsigned long long act_all =
+                activity_word<unsigned long long>((unsigned long long)x | a.prefix, a.distance, a.interval_mask);
+            const I act = (I)act_all & (I)a.flip_mask;
             double acc = 0.0;
             for (int q = 0; q < T; ++q) {
                 const int g = q < L ? q : H0 + (q - L);
@@ -81,8 +96,10 @@ __global__ void __launch_bounds__(kPassThreads) pass_kernel_generic(const PassAr
                 }
             }
             double r = a.gamma * acc;
-            if (asrc) r += a.alpha * asrc[x];
-            if (csrc) r += a.beta * csrc[x];
+            for (int k = 0; k < a.nstreams; ++k) {
+                const EpiStream& st = a.s[k];
+                if (st.bit < 0 || ((act_all >> st.bit) & 1ull)) r += st.coef * st.ptr[plane][x];
+            }
             out[x] = r;
         }
         __syncthreads();
@@ -116,25 +133,25 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Epilogue operands (a, c) are streamed through a per-thread ring of RING rows in shared memory,
-// filled by cp.async from kernel entry on: deep memory-level parallelism at no register cost.
-// pass 0 carries two operands (ring 4 + 4 rows), later passes one (ring 8): 32 KiB either way.
-constexpr int kRingRows0 = 4;
-constexpr int kRingRows1 = 8;
-constexpr int kPassSmemBytes = (8 << kTile) + 32768;
+// Epilogue operands are streamed through per-thread rings of shared memory filled by cp.async from
+// kernel entry on: deep memory-level parallelism at no register cost.  kRingRowsTotal rows of
+// 4 KiB (256 threads x 16 B) are split evenly between the NOPS operand streams of the launch.
+constexpr int kRingRowsTotal = 12;
+constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16;  // 112 KiB: 2 CTAs/SM
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
-template <typename I, int L, bool FLIP_LOW>
+// NOPS: number of epilogue streams (0..4).
+template <typename I, int L, bool FLIP_LOW, int NOPS>
 __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs a) {
     constexpr int M = kTile - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
+    constexpr int RING = NOPS ? kRingRowsTotal / NOPS : 1;
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
+    static_assert(NOPS >= 0 && NOPS <= kMaxStreams, "streams");
     extern __shared__ double tile[];
     const int plane = blockIdx.y;
     const double* __restrict__ in = a.in[plane];
-    const double* __restrict__ asrc = a.a_src[plane];
-    const double* csrc = a.c_src[plane];
     double* out = a.out[plane];
     const int H0 = a.high_start;
     const int d = a.distance;
@@ -150,20 +167,31 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     const unsigned y_thr = tid << 1;  // local bits 1..8
     const I x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
 
-    constexpr int RING = FLIP_LOW ? kRingRows0 : kRingRows1;
     double2* tile2 = reinterpret_cast<double2*>(tile);
-    double2* ring_c = tile2 + (1 << (kTile - 1));          // [RING][256]
-    double2* ring_a = ring_c + RING * kPassThreads;        // [RING][256] (pass 0 only)
+    double2* ring = tile2 + (1 << (kTile - 1));  // [NOPS][RING][256]
     auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
         const unsigned ye = (unsigned)e << kRowShift;
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
     };
-    // ---- start streaming the epilogue operands ------------------------------------------------
+    auto stream_on = [&](int k, I x) -> bool {
+        if (FLIP_LOW) return true;  // pass 0 only carries the unconditional recurrence operands
+        return (a.s[k].mask >> ((unsigned)(x >> a.s[k].shift) & 15u)) & 1u;
+    };
+    auto fetch_row = [&](int e) {  // issue the cp.async of every stream for row e into its ring slot
 #pragma unroll
-    for (int e = 0; e < RING; ++e) {
-        if (csrc) cp_async16(ring_c + e * kPassThreads + tid, csrc + row_x(e));
-        if (FLIP_LOW && asrc) cp_async16(ring_a + e * kPassThreads + tid, asrc + row_x(e));
-        cp_async_commit();
+        for (int k = 0; k < NOPS; ++k) {
+            const I x = row_x(e);
+            if (stream_on(k, x))
+                cp_async16(ring + ((k * RING + (e % RING)) * kPassThreads + tid), a.s[k].ptr[plane] + x);
+        }
+    };
+    // ---- start streaming the epilogue operands ------------------------------------------------
+    if (NOPS) {
+#pragma unroll
+        for (int e = 0; e < RING; ++e) {
+            fetch_row(e);
+            cp_async_commit();
+        }
     }
     // ---- stage the tile: 16 rows x one 16-byte pair per thread -------------------------------
     double2 v[kRows];
@@ -234,30 +262,30 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         double2 r;
         r.x = a.gamma * acc0;
         r.y = a.gamma * acc1;
-        cp_async_wait<RING - 1>();  // the group of row e has landed (own data: no barrier needed)
-        if (FLIP_LOW) {
-            if (asrc) {
-                const double2 s = ring_a[(e % RING) * kPassThreads + tid];
-                r.x = fma(a.alpha, s.x, r.x);
-                r.y = fma(a.alpha, s.y, r.y);
+        if (NOPS) {
+            cp_async_wait<RING - 1>();  // the group of row e has landed (own data: no barrier needed)
+            const I x = row_x(e);
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) {
+                if (stream_on(k, x)) {
+                    const double2 sv = ring[(k * RING + (e % RING)) * kPassThreads + tid];
+                    r.x = fma(a.s[k].coef, sv.x, r.x);
+                    r.y = fma(a.s[k].coef, sv.y, r.y);
+                }
             }
-        } else if (asrc) {  // not used by the stepper (later passes carry only c), kept for generality
-            const double2 s = ldg_stream(asrc + row_x(e));
-            r.x = fma(a.alpha, s.x, r.x);
-            r.y = fma(a.alpha, s.y, r.y);
-        }
-        if (csrc) {
-            const double2 s = ring_c[(e % RING) * kPassThreads + tid];
-            r.x = fma(a.beta, s.x, r.x);
-            r.y = fma(a.beta, s.y, r.y);
         }
         stg_stream(out + row_x(e), r);
-        if (e + RING < kRows) {  // refill the slot just consumed
-            if (csrc) cp_async16(ring_c + (e % RING) * kPassThreads + tid, csrc + row_x(e + RING));
-            if (FLIP_LOW && asrc) cp_async16(ring_a + (e % RING) * kPassThreads + tid, asrc + row_x(e + RING));
+        if (NOPS) {
+            if (e + RING < kRows) fetch_row(e + RING);  // refill the slot just consumed
+            cp_async_commit();
         }
-        cp_async_commit();
     }
 }
+
+// kernel tables, one translation unit per index type (qca_pass_u32.cu / qca_pass_u64.cu)
+typedef void (*PassKernel)(const PassArgs);
+PassKernel fast_pass_kernel_u32(int low_bits, int nstreams);
+PassKernel fast_pass_kernel_u64(int low_bits, int nstreams);
+PassKernel generic_pass_kernel(bool wide);
 
 }  // namespace qca

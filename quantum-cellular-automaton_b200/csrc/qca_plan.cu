@@ -132,6 +132,39 @@ void plan_passes(int local_bits, std::vector<qca_pass_t>& out) {
     }
 }
 
+int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_remote_op_t>& out) {
+    out.clear();
+    int rank_bits = 0;
+    while ((1 << rank_bits) < world) ++rank_bits;
+    const int n = r.ncells - rank_bits;
+    QCA_REQUIRE(n >= 1, QCA_ERR_ARG, "ncells %d too small for %d ranks", r.ncells, world);
+    std::vector<qca_pass_t> passes;
+    plan_passes(n, passes);
+    const int later = (int)passes.size() - 1;
+    const int dbits = std::min(r.distance, n);
+    const uint32_t imask = interval_mask_of(r.act_lo, r.act_hi);
+    int placed = 0;
+    for (int j = 0; j < rank_bits; ++j) {
+        qca_remote_op_t op{};
+        op.qubit = n + j;
+        op.partner = rank ^ (1 << j);
+        op.sign = ((rank >> j) & 1) ? -1 : 1;
+        op.shift = n - dbits;
+        bool any = false;
+        for (unsigned v = 0; v < (1u << dbits); ++v) {
+            const unsigned long long xf = ((unsigned long long)rank << n) | ((unsigned long long)v << op.shift);
+            const bool on = (activity_word<unsigned long long>(xf, r.distance, imask) >> op.qubit) & 1ull;
+            any |= on;
+            if (on && v < 32) op.mask |= (1u << v);
+        }
+        if (!any) continue;  // this rank never sees the term (e.g. not enough alive cells above)
+        op.pass = later > 0 ? 1 + (placed % later) : 0;
+        ++placed;
+        out.push_back(op);
+    }
+    return QCA_OK;
+}
+
 }  // namespace qca
 
 extern "C" {
@@ -168,6 +201,22 @@ int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity
     if (passes != nullptr) {
         QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "pass buffer too small");
         memcpy(passes, v.data(), v.size() * sizeof(qca_pass_t));
+    }
+    return QCA_OK;
+}
+
+int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_op_t* ops,
+                        int32_t capacity, int32_t* nops) {
+    QCA_CHECK(qca::validate_rule(rule));
+    QCA_REQUIRE(world_size == 1 || world_size == 2 || world_size == 4 || world_size == 8, QCA_ERR_ARG,
+                "world_size must be 1, 2, 4 or 8 (got %d)", world_size);
+    QCA_REQUIRE(rank >= 0 && rank < world_size && nops != nullptr, QCA_ERR_ARG, "bad rank / NULL nops");
+    std::vector<qca_remote_op_t> v;
+    QCA_CHECK(qca::plan_remote(*rule, world_size, rank, v));
+    *nops = (int32_t)v.size();
+    if (ops != nullptr) {
+        QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "remote-op buffer too small");
+        memcpy(ops, v.data(), v.size() * sizeof(qca_remote_op_t));
     }
     return QCA_OK;
 }

@@ -1,0 +1,121 @@
+"""One process per GPU: the state vector is sharded over the top log2(P) qubits, rank r holding
+the contiguous slice ``psi[r*2^n:(r+1)*2^n]`` of ``MPS.as_vector()``.
+
+``torch.distributed`` is plumbing only: it moves the 64-byte CUDA-IPC handles once at start-up,
+two booleans after a state upload and the 4*N measurement sums per measure.  The data path (terms
+that flip a sharded qubit) is peer-memory loads inside the tile-pass kernel plus a device-side flag
+barrier (csrc/qca_exact.cu); no collective runs per step.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world_and_rank(group=None) -> tuple[int, int]:
+    try:
+        dist = _dist()
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(group), dist.get_rank(group)
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def gather_objects(obj, group=None) -> list:
+    """Every rank's object, in rank order, on every rank."""
+    world, _ = world_and_rank(group)
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    _dist().all_gather_object(out, obj, group=group)
+    return out
+
+
+def local_slice(psi: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """This rank's contiguous part of a full 2^N vector (top log2(world) bits == rank)."""
+    n = psi.shape[0] // world
+    return psi[rank * n:(rank + 1) * n]
+
+
+def combine_measurements(partials: list[np.ndarray], ncells: int):
+    """Sum the per-rank partial sums in rank order (deterministic, identical on all ranks) and
+    finish them into population / rounded population / entropy / bond dimensions."""
+    total = np.zeros(4 * ncells)
+    for part in partials:
+        total += np.asarray(part, dtype=np.float64)
+    return _lib.measure_finish(total, ncells)
+
+
+class ShardedExactEngine:
+    """Same surface as ``_lib.ExactEngine`` for a register sharded over the ranks of `group`."""
+
+    def __init__(self, rules, device: int, flags: int = 0, stream: int | None = None, group=None):
+        self.group = group
+        self.world, self.rank = world_and_rank(group)
+        self.ncells = int(rules.ncells)
+        self._eng = _lib.ExactEngine(rules, device=device, world_size=self.world, rank=self.rank, flags=flags,
+                                     stream=stream)
+        self.local_amps = self._eng.local_amps
+        if self.world > 1:
+            table = np.stack(gather_objects(self._eng.ipc_handles(), group))
+            self._eng.ipc_import(table)
+
+    # -- state ---------------------------------------------------------------------------------
+    def _resolve(self) -> None:
+        if self.world == 1:
+            return
+        flags = gather_objects(self._eng.plane_flags(), self.group)
+        self._eng.resolve_planes(any(f[0] for f in flags), any(f[1] for f in flags))
+
+    def set_product_state(self, plist) -> None:
+        self._eng.set_product_state(plist)
+        self._resolve()
+
+    def set_state(self, psi) -> None:
+        """psi: the full 2^N vector (each rank takes its slice) or this rank's slice."""
+        arr = np.asarray(psi).reshape(-1)
+        if arr.size == self.local_amps * self.world and self.world > 1:
+            arr = local_slice(arr, self.world, self.rank)
+        self._eng.set_state(arr)
+        self._resolve()
+
+    def get_local_state(self) -> np.ndarray:
+        return self._eng.get_state()
+
+    def get_state(self) -> np.ndarray:
+        """The full vector on every rank (host gather; for small registers and tests)."""
+        return np.concatenate(gather_objects(self._eng.get_state(), self.group))
+
+    # -- evolution -------------------------------------------------------------------------------
+    def step(self, step_size: float, nsteps: int = 1) -> None:
+        self._eng.step(step_size, nsteps)
+
+    def measure(self):
+        if self.world == 1:
+            return self._eng.measure()
+        return combine_measurements(gather_objects(self._eng.measure_partial(), self.group), self.ncells)
+
+    def apply_h(self, vec) -> np.ndarray:
+        arr = np.asarray(vec).reshape(-1)
+        if arr.size == self.local_amps * self.world and self.world > 1:
+            arr = local_slice(arr, self.world, self.rank)
+        return np.concatenate(gather_objects(self._eng.apply_h(arr), self.group))
+
+    def norm2(self) -> float:
+        return float(sum(gather_objects(self._eng.norm2(), self.group)))
+
+    def stats(self) -> dict:
+        return self._eng.stats()
+
+    def reset_stats(self) -> None:
+        self._eng.reset_stats()
+
+    def close(self) -> None:
+        self._eng.close()
