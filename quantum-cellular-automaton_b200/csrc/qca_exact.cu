@@ -338,8 +338,11 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     int smem = (int)(sizeof(double) << T);
     const bool wide = (e->rule.ncells > 31);
     PassKernel kern = nullptr;
-    if (e->fast_path && T == kTile)
-        kern = wide ? fast_pass_kernel_u64(ps.low_bits, a.nstreams) : fast_pass_kernel_u32(ps.low_bits, a.nstreams);
+    int nunc = 0;
+    while (nunc < a.nstreams && a.s[nunc].bit < 0) ++nunc;  // unconditional streams come first
+    if (e->fast_path && T == kTile && a.nstreams <= kMaxFastStreams)
+        kern = wide ? fast_pass_kernel_u64(ps.low_bits, nunc, a.nstreams - nunc)
+                    : fast_pass_kernel_u32(ps.low_bits, nunc, a.nstreams - nunc);
     const bool fast = kern != nullptr;
     if (fast) smem = kPassSmemBytes;
     else kern = generic_pass_kernel(wide);

@@ -25,7 +25,8 @@ constexpr int kRegHigh = 4;    // local bits 9..12 are register rows
 constexpr int kRows = 1 << kRegHigh;
 constexpr int kRowShift = kTile - kRegHigh;  // 9
 
-constexpr int kMaxStreams = 4;
+constexpr int kMaxStreams = 6;       // generic kernel; the fast kernel takes at most kMaxFastStreams
+constexpr int kMaxFastStreams = 4;
 
 // One epilogue operand:  out[x] += coef * [active(x)] * ptr[x].
 // Local recurrence operands (a, c) are unconditional; a *remote* operand is the partner rank's
@@ -141,14 +142,16 @@ constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
-// NOPS: number of epilogue streams (0..4).
-template <typename I, int L, bool FLIP_LOW, int NOPS>
+// NUNC unconditional epilogue streams (recurrence operands) come first, then NCOND conditional
+// ones (remote terms of sharded qubits); NUNC + NCOND <= 4.
+template <typename I, int L, bool FLIP_LOW, int NUNC, int NCOND>
 __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs a) {
+    constexpr int NOPS = NUNC + NCOND;
     constexpr int M = kTile - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
     constexpr int RING = NOPS ? kRingRowsTotal / NOPS : 1;
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
-    static_assert(NOPS >= 0 && NOPS <= kMaxStreams, "streams");
+    static_assert(NOPS >= 0 && NOPS <= kMaxFastStreams, "streams");
     extern __shared__ double tile[];
     const int plane = blockIdx.y;
     const double* __restrict__ in = a.in[plane];
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
     };
     auto stream_on = [&](int k, I x) -> bool {
-        if (FLIP_LOW) return true;  // pass 0 only carries the unconditional recurrence operands
+        if (k < NUNC) return true;
         return (a.s[k].mask >> ((unsigned)(x >> a.s[k].shift) & 15u)) & 1u;
     };
     auto fetch_row = [&](int e) {  // issue the cp.async of every stream for row e into its ring slot
@@ -284,8 +287,8 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
 
 // kernel tables, one translation unit per index type (qca_pass_u32.cu / qca_pass_u64.cu)
 typedef void (*PassKernel)(const PassArgs);
-PassKernel fast_pass_kernel_u32(int low_bits, int nstreams);
-PassKernel fast_pass_kernel_u64(int low_bits, int nstreams);
+PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int ncond);
+PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int ncond);
 PassKernel generic_pass_kernel(bool wide);
 
 }  // namespace qca

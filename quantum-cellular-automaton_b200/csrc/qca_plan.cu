@@ -140,10 +140,8 @@ int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_re
     QCA_REQUIRE(n >= 1, QCA_ERR_ARG, "ncells %d too small for %d ranks", r.ncells, world);
     std::vector<qca_pass_t> passes;
     plan_passes(n, passes);
-    const int later = (int)passes.size() - 1;
     const int dbits = std::min(r.distance, n);
     const uint32_t imask = interval_mask_of(r.act_lo, r.act_hi);
-    int placed = 0;
     for (int j = 0; j < rank_bits; ++j) {
         qca_remote_op_t op{};
         op.qubit = n + j;
@@ -158,9 +156,30 @@ int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_re
             if (on && v < 32) op.mask |= (1u << v);
         }
         if (!any) continue;  // this rank never sees the term (e.g. not enough alive cells above)
-        op.pass = later > 0 ? 1 + (placed % later) : 0;
-        ++placed;
         out.push_back(op);
+    }
+    // Placement: NVLink reads should overlap the HBM traffic of every pass, so the terms are
+    // spread over the passes, heaviest first onto the least loaded pass.  Pass 0 already streams two
+    // recurrence operands and takes at most one term; later passes at most three.
+    const int npass = (int)passes.size();
+    std::vector<double> load(npass, 0.0);
+    std::vector<int> count(npass, 0);
+    std::vector<int> order(out.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    auto weight = [&](int i) { return (double)__builtin_popcount(out[i].mask) + (out[i].mask ? 0.0 : 1.0); };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight(x) > weight(y); });
+    for (int i : order) {
+        int best = -1;
+        for (int p = 0; p < npass; ++p) {
+            const int cap = (npass == 1) ? 8 : (p == 0 ? 1 : 3);
+            if (count[p] >= cap) continue;
+            // ties go to the later pass (its ring is deeper: one recurrence operand instead of two)
+            if (best < 0 || load[p] < load[best] - 1e-9 || (fabs(load[p] - load[best]) <= 1e-9 && p > best)) best = p;
+        }
+        if (best < 0) best = npass - 1;
+        out[i].pass = best;
+        load[best] += weight(i);
+        count[best] += 1;
     }
     return QCA_OK;
 }
