@@ -95,6 +95,7 @@ typedef struct qca_exact* qca_exact_t;
 
 #define QCA_FLAG_FORCE_COMPLEX 1u /* keep both real planes even if the rotated state is real */
 #define QCA_FLAG_PROFILE 2u       /* record a CUDA-event pair around every kernel launch */
+#define QCA_FLAG_LOOSE_BOUND 4u   /* scale H by the Gershgorin bound only (skip the block-Lanczos bound) */
 
 /* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U
  * (dense 2^N x 2^N) the engine keeps only the rule.  world_size/rank shard the
@@ -145,6 +146,11 @@ int32_t qca_exact_apply_h(qca_exact_t h, const double* in, double* out, uint64_t
 
 /* Squared norm of the resident state (this rank's slice). */
 int32_t qca_exact_norm2(qca_exact_t h, double* norm2);
+
+/* The engine scales H by a bound R of its spectral radius: min(Gershgorin, sum of block norms found
+ * by Lanczos on the device at creation).  Sharded engines must agree on R: set the maximum over
+ * ranks with this call before the first step. */
+int32_t qca_exact_set_spectral_bound(qca_exact_t h, double bound);
 
 typedef struct qca_exact_stats {
     double spectral_bound;       /* R used to scale H */

@@ -29,6 +29,7 @@ class QcaError(RuntimeError):
 QCA_OK, QCA_ERR_ARG, QCA_ERR_CUDA, QCA_ERR_NOMEM, QCA_ERR_STATE, QCA_ERR_UNSUPPORTED = range(6)
 QCA_FLAG_FORCE_COMPLEX = 1
 QCA_FLAG_PROFILE = 2
+QCA_FLAG_LOOSE_BOUND = 4
 QCA_IPC_HANDLE_BYTES = 64
 
 
@@ -83,6 +84,7 @@ SYMBOLS = {
     "qca_measure_finish": (C.c_int32, [_dp, C.c_int32, _dp, _dp, _dp, _dp]),
     "qca_exact_apply_h": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "qca_exact_norm2": (C.c_int32, [C.c_void_p, _dp]),
+    "qca_exact_set_spectral_bound": (C.c_int32, [C.c_void_p, C.c_double]),
     "qca_exact_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(ExactStats)]),
     "qca_exact_reset_stats": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
@@ -270,6 +272,9 @@ class ExactEngine:
         v = C.c_double()
         check(lib.qca_exact_norm2(self._h, C.byref(v)))
         return v.value
+
+    def set_spectral_bound(self, bound: float) -> None:
+        check(lib.qca_exact_set_spectral_bound(self._h, float(bound)))
 
     def stats(self) -> dict:
         st = ExactStats()

@@ -20,7 +20,6 @@
 
 namespace qca {
 
-
 // out = alpha * src
 __global__ void scale_kernel(double* __restrict__ out, const double* __restrict__ src, double alpha,
                              unsigned long long n) {
@@ -594,6 +593,139 @@ static int32_t measure_partial(Engine* e, double* sums) {
     return QCA_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Tight spectral bound.  ||H|| <= sum over blocks of consecutive cells of ||H_block||, where
+// H_block keeps only the terms whose flipped cell lies in the block (it acts on the block plus
+// `distance` context cells on each inner side).  Each block norm is the top Ritz value of a
+// Lanczos run on the block's antisymmetric K (alpha_j = 0: q_{j+1} b_{j+1} = K q_j + b_j q_{j-1}),
+// executed on the device with the engine's own kernels on a register of at most kBoundSites
+// qubits; the tridiagonal eigenvalue is found on the host by Sturm bisection.  For the
+// N=30, distance 2, [2,4) workload this gives R = 22.7 instead of the Gershgorin 30.
+// ---------------------------------------------------------------------------
+struct Engine;
+static Engine* engine_of(qca_exact_t h);
+
+constexpr int kBoundSites = 20;
+constexpr int kLanczosMax = 160;
+
+static double tridiag_top_eigenvalue(const std::vector<double>& b) {
+    // symmetric tridiagonal, zero diagonal, off-diagonals b[0..m-2]  (m = b.size() + 1)
+    const int m = (int)b.size() + 1;
+    if (m == 1) return 0.0;
+    double hi = 0.0;
+    for (int i = 0; i < m; ++i) hi = std::max(hi, (i > 0 ? fabs(b[i - 1]) : 0.0) + (i < m - 1 ? fabs(b[i]) : 0.0));
+    double lo = 0.0;
+    auto count_below = [&](double x) {  // number of eigenvalues < x
+        int cnt = 0;
+        double q = -x;
+        if (q < 0) ++cnt;
+        for (int i = 1; i < m; ++i) {
+            if (q == 0.0) q = 1e-300;
+            q = -x - b[i - 1] * b[i - 1] / q;
+            if (q < 0) ++cnt;
+        }
+        return cnt;
+    };
+    for (int it = 0; it < 100; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (count_below(mid) >= m) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+// Norm of the block operator on a register of `nsites` qubits with flipped qubits `centers`.
+static int32_t block_norm(const qca_rule_t& rule, int nsites, unsigned long long centers, int device,
+                          double* norm_out, uint64_t* launches) {
+    qca_rule_t sub = rule;
+    sub.ncells = nsites;
+    qca_exact_t h = nullptr;
+    QCA_CHECK(qca_exact_create(&h, &sub, device, 1, 0, QCA_FLAG_LOOSE_BOUND, nullptr));
+    Engine* e = engine_of(h);
+    int32_t rc = QCA_OK;
+    do {
+        e->fast_path = false;  // the generic kernel honours flip_mask
+        for (auto& ps : e->passes) ps.flip_mask &= centers;
+        for (int v = 0; v < 3; ++v) if ((rc = ensure_plane(e, v, 0))) break;
+        if (rc) break;
+        e->nplanes = 1; e->resolved = true; e->cur = 0;
+        std::vector<double> start((size_t)e->namps);
+        unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+        double nrm = 0.0;
+        for (auto& x : start) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            x = (double)(long long)(lcg >> 11) / 9007199254740992.0 - 0.5;
+            nrm += x * x;
+        }
+        nrm = 1.0 / sqrt(nrm);
+        for (auto& x : start) x *= nrm;
+        if (cudaMemcpyAsync(e->plane[1][0], start.data(), e->plane_bytes(), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess) { set_error("bound: upload failed"); rc = QCA_ERR_CUDA; break; }
+        int prev = 0, cur = 1;  // q_{j-1} (overwritten by w), q_j
+        std::vector<double> beta;
+        double bj = 0.0, theta = 0.0, theta_old = -1.0;
+        for (int j = 0; j < kLanczosMax; ++j) {
+            // w = b_j q_{j-1} + K q_j, written over q_{j-1}
+            if ((rc = apply_operator(e, prev, cur, -1, 0.0, j == 0 ? -1 : prev, bj, 1.0))) break;
+            e->cur = prev;
+            double n2 = 0.0;
+            if ((rc = qca_exact_norm2(h, &n2))) break;
+            const double bn = sqrt(n2);
+            if (!(bn > 1e-12)) break;  // invariant subspace: the Ritz values are exact
+            beta.push_back(bn);
+            if ((rc = launch_scale(e, prev, prev, 1.0 / bn))) break;
+            std::swap(prev, cur);      // cur = q_{j+1}, prev = q_j
+            bj = bn;
+            if ((j % 8) == 7 || j == kLanczosMax - 1) {
+                theta = tridiag_top_eigenvalue(beta);
+                if (theta_old > 0 && fabs(theta - theta_old) <= 1e-10 * theta) break;
+                theta_old = theta;
+            }
+        }
+        if (rc) break;
+        theta = tridiag_top_eigenvalue(beta);
+        *norm_out = theta;
+        if (launches) *launches += e->st.kernel_launches;
+    } while (0);
+    qca_exact_destroy(h);
+    return rc;
+}
+
+static int32_t tight_spectral_bound(const qca_rule_t& rule, int device, double* bound) {
+    const int n = rule.ncells, d = rule.distance;
+    // fewest blocks such that every block register fits kBoundSites qubits
+    int nb = 1;
+    for (;; ++nb) {
+        const int bmax = (n + nb - 1) / nb;
+        const int sites = (nb == 1) ? n : (nb == 2 ? bmax + d : bmax + 2 * d);
+        if (sites <= kBoundSites || bmax <= 1) break;
+    }
+    std::vector<int> sizes(nb, n / nb);
+    // larger blocks at the two ends (they need context on one side only)
+    for (int i = 0, extra = n % nb; extra > 0; --extra, ++i) sizes[(i % 2) ? nb - 1 - i / 2 : i / 2] += 1;
+    double total = 0.0;
+    std::vector<std::pair<long long, double>> cache;  // (kind * 64 + size) -> norm
+    for (int i = 0; i < nb; ++i) {
+        const bool low_end = (i == 0), high_end = (i == nb - 1);
+        const int B = sizes[i];
+        const int kind = (low_end && high_end) ? 0 : ((low_end || high_end) ? 1 : 2);  // mirror: both ends alike
+        const long long key = kind * 64 + B;
+        double val = -1.0;
+        for (auto& c : cache) if (c.first == key) val = c.second;
+        if (val < 0.0) {
+            const int ctx_low = (kind == 2) ? d : 0;          // an end block is computed as the low end
+            const int ctx_high = (kind == 0) ? 0 : d;
+            const int sites = ctx_low + B + ctx_high;
+            const unsigned long long centers = ((1ull << B) - 1ull) << ctx_low;
+            QCA_CHECK(block_norm(rule, sites, centers, device, &val, nullptr));
+            cache.emplace_back(key, val);
+        }
+        total += val;
+    }
+    *bound = total * (1.0 + 1e-3);  // Lanczos converges from below; 0.1 % covers the residual
+    return QCA_OK;
+}
+
 }  // namespace qca
 
 using qca::Engine;
@@ -601,6 +733,10 @@ using qca::Engine;
 struct qca_exact {
     Engine e;
 };
+
+namespace qca {
+static Engine* engine_of(qca_exact_t h) { return &h->e; }
+}  // namespace qca
 
 extern "C" {
 
@@ -660,6 +796,13 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
               cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
     if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
+    if (!(flags & QCA_FLAG_LOOSE_BOUND)) {
+        double tight = e->bound;
+        if (int32_t rc = qca::tight_spectral_bound(*rule, device, &tight)) { qca_exact_destroy(h); return rc; }
+        QCA_CUDA(cudaSetDevice(device));
+        if (tight < e->bound) e->bound = tight;
+        e->st.spectral_bound = e->bound;
+    }
     if (world_size > 1) {
         // every plane exists up front so that it can be exported once
         for (int v = 0; v < 3; ++v)
@@ -854,6 +997,14 @@ int32_t qca_exact_norm2(qca_exact_t h, double* norm2) {
     QCA_CUDA(cudaMemcpyAsync(hsum, e->d_sums, sizeof(hsum), cudaMemcpyDeviceToHost, e->stream));
     QCA_CUDA(cudaStreamSynchronize(e->stream));
     *norm2 = hsum[0] + hsum[1];
+    return QCA_OK;
+}
+
+int32_t qca_exact_set_spectral_bound(qca_exact_t h, double bound) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    QCA_REQUIRE(bound > 0.0 && isfinite(bound), QCA_ERR_ARG, "spectral bound must be positive");
+    h->e.bound = bound;
+    h->e.st.spectral_bound = bound;
     return QCA_OK;
 }
 

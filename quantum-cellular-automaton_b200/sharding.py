@@ -66,6 +66,8 @@ class ShardedExactEngine:
         if self.world > 1:
             table = np.stack(gather_objects(self._eng.ipc_handles(), group))
             self._eng.ipc_import(table)
+            # every rank must scale H by the same bound (they computed it independently)
+            self._eng.set_spectral_bound(max(gather_objects(self._eng.stats()["spectral_bound"], group)))
 
     # -- state ---------------------------------------------------------------------------------
     def _resolve(self) -> None:

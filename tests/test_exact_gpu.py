@@ -209,3 +209,33 @@ def test_zero_step_is_identity_and_stats_count_launches():
     assert st["passes_per_apply"] == 2 and st["last_terms"] > 10
     assert st["pass_launches"] == (st["last_terms"] - 1) * 2
     assert st["profiled_pass_launches"] == st["pass_launches"] and st["profiled_pass_ms"] > 0.0
+
+
+@pytest.mark.parametrize("n,d,lo,hi", [(9, 1, 1, 2), (11, 2, 2, 4), (10, 1, 1, 3), (8, 3, 2, 5), (3, 1, 1, 2)])
+def test_tight_spectral_bound_is_a_bound(n, d, lo, hi):
+    """The block-Lanczos bound the engine scales H by is above the true spectral radius (dense
+    oracle), below Gershgorin, and within a few per cent of the truth when one block covers the chain."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    true_radius = np.linalg.eigvalsh(oracle.rule_hamiltonian_direct(n, d, lo, hi)).max()
+    eng = _lib.ExactEngine(rules)
+    loose = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_LOOSE_BOUND)
+    tight_r, loose_r = eng.stats()["spectral_bound"], loose.stats()["spectral_bound"]
+    assert loose_r == _lib.spectral_bound(rules)
+    assert true_radius <= tight_r <= loose_r + 1e-12
+    assert tight_r <= true_radius * 1.002 + 1e-9
+    # both scalings evolve to the same state
+    plist = qca_b200.states.plist("single", rules)
+    eng.set_product_state(plist), loose.set_product_state(plist)
+    eng.step(1.0, 2), loose.step(1.0, 2)
+    assert np.abs(eng.get_state() - loose.get_state()).max() < 1e-12
+    assert eng.stats()["last_terms"] <= loose.stats()["last_terms"]
+
+
+def test_tight_bound_large_chain_blocks():
+    rules = qca_b200.Rules(26, range(2, 4), 2)
+    eng = _lib.ExactEngine(rules)
+    r = eng.stats()["spectral_bound"]
+    assert 0.70 * 26 < r < 0.80 * 26  # ~0.76 per cell for this rule (two end blocks of 13)
+    eng.set_product_state(qca_b200.states.plist("triple_blinker", rules))
+    eng.step(1.0, 1)
+    assert abs(eng.norm2() - 1.0) < 1e-12
