@@ -7,8 +7,8 @@ Import as ``qca_b200`` (see ``qca_b200.py`` at the repository root).
 """
 from .parameters import Rules, Args
 from .tensor_networks import MPS, MPO
-from .algorithms import Algorithm, Exact
+from .algorithms import Algorithm, Exact, TDVP
 from . import states
 from ._lib import lib, QcaError, library_path
 
-__all__ = ["Rules", "Args", "MPS", "MPO", "Algorithm", "Exact", "states", "lib", "QcaError", "library_path"]
+__all__ = ["Rules", "Args", "MPS", "MPO", "Algorithm", "Exact", "TDVP", "states", "lib", "QcaError", "library_path"]

@@ -1,4 +1,5 @@
 from .algorithm import Algorithm
 from .exact import Exact
+from .tdvp import TDVP
 
-__all__ = ["Algorithm", "Exact"]
+__all__ = ["Algorithm", "Exact", "TDVP"]

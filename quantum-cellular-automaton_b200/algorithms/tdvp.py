@@ -1,0 +1,317 @@
+"""``TDVP``: one- and two-site time-dependent variational principle on one GPU, drop-in for
+algorithms/tdvp.py:9-146 (``--algorithm 1tdvp | 2tdvp``).
+
+The reference assembles every effective Hamiltonian as a dense (d*Dl*Dr)^2 matrix
+(tdvp.py:299-310, 352-359) and exponentiates it by ``eigh`` (lautils.py:58-82), which limits it
+to bond dimension ~32.  Here the MPS, the MPO and the environments live on the device and
+
+* H_eff is applied matrix-free:  out[b,y,v] = sum W[a,b,wl,wr] L[x,wl,y] R[u,wr,v] psi[a,x,u]
+  in the L.psi -> W -> .R order (8 w chi^3 complex MACs for a two-site tensor instead of 16 chi^4),
+* exp(-i pi/2 delta H_eff) psi comes from a Lanczos recursion that never leaves the device (Krylov
+  dimension fixed from |delta| * spectral bound, no host synchronisation inside a sweep); tensors
+  small enough for a dense solve (dimension <= DENSE_LIMIT) take the reference's exact route,
+* QR / SVD / truncation run on the device (cuSOLVER through torch.linalg).
+
+Index conventions are the reference's: ``A[p,l,r]``, ``W[a,b,wl,wr]``, environments ``L[x,w,y]`` /
+``R[u,w,v]`` with x/u on the ket side.  Same sweep order, same truncation rule
+(tdvp.py:289-296), same gauge handling (mps.py:146-192) as the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .algorithm import Algorithm
+from .. import _lib
+from ..tensor_networks import MPS, MPO
+
+DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
+KRYLOV_TOL = 1e-16
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def krylov_dimension(rho: float) -> int:
+    """Smallest m with (rho/2)^m / m! below KRYLOV_TOL (error bound of the m-step Lanczos
+    approximation of exp(-i t H) v for |t| * ||H|| = rho)."""
+    m, term = 1, rho / 2.0
+    while term > KRYLOV_TOL and m < 64:
+        m += 1
+        term *= (rho / 2.0) / m
+    return max(m + 1, 4)
+
+
+class TDVP(Algorithm):
+
+    def __init__(self, psi_0: MPS, H: MPO, args, *, device: int = 0) -> None:
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.QcaError(_lib.QCA_ERR_CUDA, "TDVP needs a CUDA device; there is no CPU fallback")
+        self.dev = torch.device("cuda", device)
+        self.ct = torch.complex128
+        if args.algorithm not in ("1tdvp", "2tdvp"):
+            raise NotImplementedError(f"algorithm {args.algorithm!r}: only 1tdvp and 2tdvp are implemented on the GPU")
+        self._W = [torch.as_tensor(np.ascontiguousarray(w), dtype=self.ct, device=self.dev) for w in H.W]
+        # ||H_eff|| <= ||H|| <= R: the Krylov dimension follows from |delta| * pi/2 * R
+        self._bound = _lib.spectral_bound(args.rules)
+        super().__init__(psi_0, H, args)
+        n = len(self._A)
+        self._canonicalize(n - 1)  # tdvp.py:23-26: fix the bond dimensions, then right-orthonormal form
+        self._canonicalize(0)
+        self._left: list = [None] * n
+        self._right: list = [None] * n
+        self._max_bond_dims = [min(2 ** i, 2 ** (n - i), args.max_bond_dim) for i in range(n + 1)]
+        self._target_bond_dims = list(self._max_bond_dims)
+        self._one = torch.ones((1, 1, 1), dtype=self.ct, device=self.dev)
+        for site in reversed(range(1, n)):  # tdvp.py:37-39
+            self._canonicalize(site - 1)
+            self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+        self.heff_applications = 0
+
+    # -- Algorithm interface ----------------------------------------------------------------
+    @property
+    def psi(self) -> MPS:
+        return MPS([a.cpu().numpy() for a in self._A])
+
+    @psi.setter
+    def psi(self, value: MPS) -> None:
+        torch = _torch()
+        self._A = [torch.as_tensor(np.ascontiguousarray(a), dtype=self.ct, device=self.dev) for a in value.A]
+
+    def measure(self, population, d_population, single_site_entropy, bond_dims) -> None:
+        """MPS.measure (mps.py:100-140): sweep the orthogonality centre through the chain on the
+        device, one D2H copy of the N reduced density matrices at the end."""
+        torch = _torch()
+        n = len(self._A)
+        assert n + 1 == len(bond_dims)
+        bond_dims[:n] = [a.shape[1] for a in self._A]
+        bond_dims[n] = self._A[-1].shape[2]
+        self._canonicalize(0)
+        rhos = []
+        for site in range(n):
+            if site > 0:
+                self._shift_right(site - 1)
+            a = self._A[site].reshape(2, -1)
+            rhos.append(a @ a.conj().T)
+        rho = torch.stack(rhos).cpu().numpy()
+        pop = rho[:, 1, 1].real
+        population[...] = pop
+        d_population[...] = np.round(pop)
+        lam = np.linalg.eigvalsh(rho)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            single_site_entropy[...] = -np.where(lam > 0, lam * np.log2(np.where(lam > 0, lam, 1.0)), 0.0).sum(axis=1)
+
+    def do_time_step(self) -> None:
+        """tdvp.py:50-63."""
+        self._canonicalize(0)
+        if self.args.algorithm == "2tdvp":
+            self._sweep_right_two_site()
+            self._sweep_left_two_site()
+        else:
+            self._sweep_right_one_site()
+            self._sweep_left_one_site()
+
+    # -- gauge (mps.py:84-98, 146-192, 227-236) ---------------------------------------------------
+    def _fit(self, t, shape):
+        torch = _torch()
+        if all(b >= a for a, b in zip(shape, t.shape)):
+            return t[tuple(slice(0, a) for a in shape)]
+        out = torch.zeros(shape, dtype=t.dtype, device=t.device)
+        cut = tuple(slice(0, min(a, b)) for a, b in zip(shape, t.shape))
+        out[cut] = t[cut]
+        return out
+
+    def _left_qr(self, a, reduced=True):
+        torch = _torch()
+        s = a.shape
+        q, r = torch.linalg.qr(a.reshape(s[0] * s[1], s[2]), mode="reduced" if reduced else "complete")
+        return q.reshape(s[0], s[1], -1), r
+
+    def _right_qr(self, a, reduced=True):
+        q, r = self._left_qr(a.permute(0, 2, 1), reduced)
+        return q.permute(0, 2, 1), r.T
+
+    def _shift_right(self, i):
+        torch = _torch()
+        a = self._A[i]
+        q, r = self._left_qr(a)
+        self._A[i] = self._fit(q, a.shape)
+        r = self._fit(r, (a.shape[2], self._A[i + 1].shape[1]))
+        self._A[i + 1] = torch.einsum("xl,plr->pxr", r, self._A[i + 1])
+
+    def _shift_left(self, i):
+        torch = _torch()
+        a = self._A[i]
+        q, r = self._right_qr(a)
+        self._A[i] = self._fit(q, a.shape)
+        r = self._fit(r, (self._A[i - 1].shape[2], a.shape[1]))
+        self._A[i - 1] = torch.einsum("plr,rx->plx", self._A[i - 1], r)
+
+    def _canonicalize(self, i):
+        for j in range(i):
+            self._shift_right(j)
+        for j in reversed(range(i + 1, len(self._A))):
+            self._shift_left(j)
+
+    # -- environments (tdvp.py:329-347) ---------------------------------------------------------------
+    def _env_left(self, site):
+        return self._one if site < 0 else self._left[site]
+
+    def _env_right(self, site):
+        return self._one if site >= len(self._A) else self._right[site]
+
+    def _grow_left(self, prev, a, w):
+        torch = _torch()
+        t = torch.einsum("xwy,axr->awyr", prev, a)
+        t = torch.einsum("abwm,awyr->bmyr", w, t)
+        return torch.einsum("bmyr,bys->rms", t, a.conj())
+
+    def _grow_right(self, prev, a, w):
+        torch = _torch()
+        t = torch.einsum("uwv,alu->awvl", prev, a)
+        t = torch.einsum("abmw,awvl->bmvl", w, t)
+        return torch.einsum("bmvl,bkv->lmk", t, a.conj())
+
+    # -- effective Hamiltonians, matrix-free ------------------------------------------------------------
+    def _apply_one_site(self, left, right, w, psi):
+        torch = _torch()
+        self.heff_applications += 1
+        t = torch.einsum("xwy,axu->awyu", left, psi)
+        t = torch.einsum("abwm,awyu->bmyu", w, t)
+        return torch.einsum("bmyu,umv->byv", t, right)
+
+    def _apply_two_site(self, left, right, w1, w2, theta):
+        torch = _torch()
+        self.heff_applications += 1
+        t = torch.einsum("xwy,acxu->acwyu", left, theta)
+        t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
+        t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)
+        return torch.einsum("bdnyu,unv->bdyv", t, right)
+
+    def _apply_bond(self, left, right, c):
+        torch = _torch()
+        t = torch.einsum("xwy,xu->wyu", left, c)
+        return torch.einsum("wyu,uwv->yv", t, right)
+
+    # -- exponentials (lautils.py:58-82) ------------------------------------------------------------------
+    def _expm_apply(self, apply, psi, delta):
+        """exp(-i pi/2 delta H_eff)^T psi in the reference's index convention: `apply` already is
+        the transposed action (psi contracted with the row index of the reference's H_eff)."""
+        torch = _torch()
+        dim = psi.numel()
+        t = (math.pi / 2.0) * delta
+        if dim <= DENSE_LIMIT:
+            eye = torch.eye(dim, dtype=self.ct, device=self.dev).reshape((dim,) + tuple(psi.shape))
+            h = torch.stack([apply(eye[k]).reshape(-1) for k in range(dim)], dim=1)  # column k = H e_k
+            h = 0.5 * (h + h.conj().T)
+            lam, vec = torch.linalg.eigh(h)
+            phase = torch.exp(-1j * t * lam)
+            return ((vec * phase) @ (vec.conj().T @ psi.reshape(-1))).reshape(psi.shape)
+        m = min(krylov_dimension(abs(t) * self._bound), dim)
+        basis = torch.zeros((m,) + tuple(psi.shape), dtype=self.ct, device=self.dev)
+        alpha = torch.zeros(m, dtype=torch.float64, device=self.dev)
+        beta = torch.zeros(m, dtype=torch.float64, device=self.dev)
+        norm0 = torch.linalg.vector_norm(psi)
+        basis[0] = psi / norm0
+        flat = basis.reshape(m, -1)
+        for j in range(m):
+            wv = apply(basis[j]).reshape(-1)
+            alpha[j] = torch.vdot(flat[j], wv).real
+            # full re-orthogonalisation (twice is enough): m is small, this is two thin GEMVs
+            for _ in range(2):
+                wv = wv - flat[: j + 1].T @ (flat[: j + 1].conj() @ wv)
+            if j + 1 < m:
+                b = torch.linalg.vector_norm(wv)
+                ok = b > 1e-13
+                beta[j + 1] = torch.where(ok, b, torch.zeros_like(b))
+                flat[j + 1] = torch.where(ok, wv / torch.where(ok, b, torch.ones_like(b)), torch.zeros_like(wv))
+        tri = torch.diag(alpha) + torch.diag(beta[1:], 1) + torch.diag(beta[1:], -1)
+        lam, vec = torch.linalg.eigh(tri)
+        coef = (vec * torch.exp(-1j * t * lam)) @ vec[0, :].to(self.ct)  # exp(-i t T) e_0
+        return norm0 * torch.tensordot(coef.to(self.ct), basis, dims=1)
+
+    def _evolve_site(self, site, delta):
+        left, right, w = self._env_left(site - 1), self._env_right(site + 1), self._W[site]
+        return self._expm_apply(lambda v: self._apply_one_site(left, right, w, v), self._A[site], delta)
+
+    # -- two-site TDVP (tdvp.py:107-145, 271-296) ---------------------------------------------------------
+    def _two_site(self, i, j):
+        torch = _torch()
+        al, ar = self._A[i], self._A[j]
+        left, right = self._env_left(i - 1), self._env_right(j + 1)
+        w1, w2 = self._W[i], self._W[j]
+        theta = torch.einsum("alm,bmr->ablr", al, ar)
+        new = self._expm_apply(lambda v: self._apply_two_site(left, right, w1, w2, v), theta, self.args.step_size / 2)
+        dl, dr = al.shape[1], ar.shape[2]
+        mat = new.permute(0, 2, 1, 3).reshape(2 * dl, 2 * dr)
+        u, s, vh = torch.linalg.svd(mat, full_matrices=False)
+        # tdvp.py:290-292: first k with ||s[k:]|| < epsilon, capped by max_bond_dim
+        tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]))
+        below = (tail < self.args.svd_epsilon).nonzero()
+        cap = min(self.args.max_bond_dim, s.shape[0])
+        keep = min(int(below[0, 0]) if below.numel() else cap, cap)
+        ul = u.reshape(2, dl, -1)[:, :, :keep]
+        vr = vh.reshape(-1, 2, dr).permute(1, 0, 2)[:, :keep, :]
+        sk = s[:keep] / torch.linalg.vector_norm(s[:keep])
+        return ul, sk.to(self.ct), vr
+
+    def _sweep_right_two_site(self):
+        torch = _torch()
+        n = len(self._A)
+        for site in range(n - 1):
+            ul, s, vr = self._two_site(site, site + 1)
+            self._A[site] = ul.contiguous()
+            self._A[site + 1] = (s[None, :, None] * vr).contiguous()
+            if site < n - 2:
+                self._left[site] = self._grow_left(self._env_left(site - 1), self._A[site], self._W[site])
+                self._A[site + 1] = self._evolve_site(site + 1, -self.args.step_size / 2)
+
+    def _sweep_left_two_site(self):
+        n = len(self._A)
+        for site in reversed(range(1, n)):
+            ul, s, vr = self._two_site(site - 1, site)
+            self._A[site] = vr.contiguous()
+            self._A[site - 1] = (ul * s[None, None, :]).contiguous()
+            if site > 1:
+                self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+                self._A[site - 1] = self._evolve_site(site - 1, -self.args.step_size / 2)
+
+    # -- one-site TDVP (tdvp.py:65-105, 164-188) -----------------------------------------------------------
+    def _evolve_bond(self, left, right, c):
+        return self._expm_apply(lambda v: self._apply_bond(left, right, v), c, -self.args.step_size / 2)
+
+    def _sweep_right_one_site(self):
+        torch = _torch()
+        n = len(self._A)
+        for site in range(n):
+            shape = (2, self._target_bond_dims[site], self._target_bond_dims[site + 1])
+            new = self._evolve_site(site, self.args.step_size / 2)
+            if site == n - 1:
+                self._A[site] = new
+                continue
+            q, c = self._left_qr(new, reduced=False)
+            self._A[site] = self._fit(q, shape).contiguous()
+            self._left[site] = self._grow_left(self._env_left(site - 1), self._A[site], self._W[site])
+            c = self._fit(c, (shape[2], c.shape[1]))
+            c = self._evolve_bond(self._env_left(site), self._env_right(site + 1), c)
+            self._A[site + 1] = torch.einsum("xl,plr->pxr", c, self._A[site + 1])
+
+    def _sweep_left_one_site(self):
+        torch = _torch()
+        n = len(self._A)
+        for site in reversed(range(n)):
+            shape = (2, self._target_bond_dims[site], self._target_bond_dims[site + 1])
+            new = self._evolve_site(site, self.args.step_size / 2)
+            if site == 0:
+                self._A[site] = new
+                continue
+            q, c = self._right_qr(new, reduced=False)
+            self._A[site] = self._fit(q, shape).contiguous()
+            self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+            c = self._fit(c, (c.shape[0], shape[1]))
+            c = self._evolve_bond(self._env_left(site - 1), self._env_right(site), c)
+            self._A[site - 1] = torch.einsum("plr,rx->plx", self._A[site - 1], c)

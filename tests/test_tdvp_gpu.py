@@ -1,0 +1,98 @@
+"""GPU parity tests of the TDVP plug-in (1tdvp / 2tdvp) against the fixtures produced by the
+unmodified reference and against the CPU oracle, at the same bond cap and SVD cutoff.
+
+Tolerance 1e-8 on populations and entropies (BASELINE.json north_star) for well-conditioned inputs.
+For exact 0/1 product states the reference's own output is only reproducible to ~1e-6 (a 1e-15
+perturbation of its input moves its populations by 5e-7; see tests/test_tdvp_oracle.py and
+DESIGN.md "TDVP parity"), so those fixtures are compared at that level.
+"""
+import numpy as np
+import pytest
+
+import qca_b200
+import tdvp_oracle
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+WELL_CONDITIONED = ("eqsup", "gradient")
+
+
+def replay(spec, g, algorithm_cls=None):
+    """quantum_game.py:82-119 with the B200 TDVP in place of the reference's."""
+    rules = qca_b200.Rules(spec["ncells"], range(spec["lo"], spec["hi"]), spec["distance"])
+    args = qca_b200.Args(rules=rules, step_size=spec["step_size"], algorithm=spec["algorithm"],
+                         max_bond_dim=spec["chi"], svd_epsilon=spec["eps"], num_steps=spec["num_steps"],
+                         plot_frequency=spec["plot_freq"])
+    assert args.plot_step_interval == int(g["plot_step_interval"])
+    algo = qca_b200.TDVP(qca_b200.states.make(spec["state"], rules), qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    steps, n = g["population"].shape
+    pop, dpop, sse, bond = np.zeros((steps, n)), np.zeros((steps, n)), np.zeros((steps, n)), np.zeros((steps, n + 1))
+    for step in range(args.num_steps):
+        if step % args.plot_step_interval == 0:
+            k = step // args.plot_step_interval
+            algo.measure(pop[k, :], dpop[k, :], sse[k, :], bond[k, :])
+        algo.do_time_step()
+    return pop, sse, bond, algo
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if any(k in n for k in WELL_CONDITIONED)])
+def test_tdvp_matches_reference_run(name):
+    spec, g = load_golden(name)
+    pop, sse, bond, algo = replay(spec, g)
+    assert np.array_equal(bond, g["bond_dims"])
+    assert np.abs(pop - g["population"]).max() < 1e-8
+    assert np.abs(sse - g["single_site_entropy"]).max() < 1e-8
+    psi = algo.psi
+    assert psi.is_valid_mps()
+    # same state up to nothing: the reference's final vector, overlap 1
+    assert abs(abs(np.vdot(psi.as_vector(), g["psi_final"])) - 1.0) < 1e-8
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if not any(k in n for k in WELL_CONDITIONED)])
+def test_tdvp_basis_states_within_reference_reproducibility(name):
+    spec, g = load_golden(name)
+    pop, sse, bond, algo = replay(spec, g)
+    assert np.abs(pop - g["population"]).max() < 2e-5
+    assert np.abs(sse - g["single_site_entropy"]).max() < 2e-4
+    assert np.abs(bond - g["bond_dims"]).max() <= 1
+
+
+@pytest.mark.parametrize("algorithm", ["2tdvp", "1tdvp"])
+def test_tdvp_lanczos_path_vs_oracle(algorithm):
+    """Bond dimension large enough that the effective dimension exceeds the dense limit, so the
+    on-device Lanczos exponential is what is being compared with the oracle's dense eigh."""
+    n, d, lo, hi, chi, eps, dt, steps = 10, 1, 1, 2, 12, 1e-9, 0.01, 12
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    args = qca_b200.Args(rules=rules, step_size=dt, algorithm=algorithm, max_bond_dim=chi, svd_epsilon=eps)
+    algo = qca_b200.TDVP(qca_b200.states.make("gradient", rules), qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    pop_o, ent_o, bond_o, psi_o = tdvp_oracle.run_tdvp("gradient", n, d, lo, hi, algorithm, dt, steps, 1, chi, eps)
+    for k in range(steps):
+        pop, dpop, ent, bond = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n + 1)
+        algo.measure(pop, dpop, ent, bond)
+        assert np.array_equal(bond, bond_o[k]), (k, bond, bond_o[k])
+        assert np.abs(pop - pop_o[k]).max() < 1e-8 and np.abs(ent - ent_o[k]).max() < 1e-8
+        algo.do_time_step()
+    assert max(a.shape[1] for a in algo.psi.A) > 4 and algo.heff_applications > 0
+    assert abs(abs(np.vdot(algo.psi.as_vector(), psi_o)) - 1.0) < 1e-8
+
+
+def test_tdvp_agrees_with_exact_when_bond_cap_is_not_binding():
+    """Untruncated 2TDVP is exact up to the Trotter-like splitting error of the sweep; with a small
+    step it tracks the exact GPU evolution closely (physics cross-check between the two plug-ins)."""
+    n = 8
+    rules = qca_b200.Rules(n, range(1, 2), 1)
+    args_t = qca_b200.Args(rules=rules, step_size=0.005, algorithm="2tdvp", max_bond_dim=16, svd_epsilon=1e-12)
+    tdvp = qca_b200.TDVP(qca_b200.states.make("gradient", rules), qca_b200.MPO.hamiltonian_from_rules(rules), args_t)
+    exact = qca_b200.Exact(qca_b200.states.make("gradient", rules), None, qca_b200.Args(rules=rules, step_size=0.005))
+    for _ in range(20):
+        tdvp.do_time_step()
+    exact.do_time_steps(20)
+    overlap = abs(np.vdot(tdvp.psi.as_vector(), exact.state_vector()))
+    assert overlap > 1 - 1e-6
+
+
+def test_tdvp_rejects_unsupported_algorithm():
+    rules = qca_b200.Rules(6, range(1, 2), 1)
+    with pytest.raises(NotImplementedError):
+        qca_b200.TDVP(qca_b200.states.make("single", rules), qca_b200.MPO.hamiltonian_from_rules(rules),
+                      qca_b200.Args(rules=rules, algorithm="a1tdvp"))
