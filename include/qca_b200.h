@@ -170,6 +170,15 @@ int32_t qca_exact_get_stats(qca_exact_t h, qca_exact_stats_t* out);
 int32_t qca_exact_reset_stats(qca_exact_t h);
 
 /* ------------------------------------------------------------------------
+ * TDVP support: Householder QR with LAPACK's conventions (numpy.linalg.qr as used by
+ * MPS.left_qr_tensors, tensor_networks/mps.py:84-88): beta = -sign(Re alpha)*norm (zlarfg), Q = H_1...H_k.
+ * All pointers are DEVICE pointers to column-major complex128.  a (m x n) is overwritten by the
+ * factorisation; q receives m x kq (kq = min(m,n) "reduced" or m "complete"), r receives kq x n.
+ * The reference's results depend on this sign convention (see csrc/qca_linalg.cu).
+ * ---------------------------------------------------------------------- */
+int32_t qca_qr_householder(void* a, int32_t m, int32_t n, void* tau, void* q, int32_t kq, void* r, void* stream);
+
+/* ------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The state is sharded over the top
  * log2(world_size) qubits; terms that flip a sharded qubit read the partner
  * rank's vector directly over NVLink (CUDA IPC peer mapping).  The host side

@@ -87,6 +87,8 @@ SYMBOLS = {
     "qca_exact_set_spectral_bound": (C.c_int32, [C.c_void_p, C.c_double]),
     "qca_exact_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(ExactStats)]),
     "qca_exact_reset_stats": (C.c_int32, [C.c_void_p]),
+    "qca_qr_householder": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -10,7 +10,8 @@ to bond dimension ~32.  Here the MPS, the MPO and the environments live on the d
 * exp(-i pi/2 delta H_eff) psi comes from a Lanczos recursion that never leaves the device (Krylov
   dimension fixed from |delta| * spectral bound, no host synchronisation inside a sweep); tensors
   small enough for a dense solve (dimension <= DENSE_LIMIT) take the reference's exact route,
-* QR / SVD / truncation run on the device (cuSOLVER through torch.linalg).
+* QR runs on the device with LAPACK's Householder conventions (csrc/qca_linalg.cu -- the
+  reference's numbers depend on them), SVD / truncation on the device through torch.linalg.
 
 Index conventions are the reference's: ``A[p,l,r]``, ``W[a,b,wl,wr]``, environments ``L[x,w,y]`` /
 ``R[u,w,v]`` with x/u on the ket side.  Same sweep order, same truncation rule
@@ -24,6 +25,7 @@ import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
+from ..linalg import householder_qr
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
@@ -126,9 +128,10 @@ class TDVP(Algorithm):
         return out
 
     def _left_qr(self, a, reduced=True):
-        torch = _torch()
+        # LAPACK-convention Householder QR: the reference's results depend on the signs of R's
+        # diagonal (the environments are not refreshed after re-canonicalisation, tdvp.py:54)
         s = a.shape
-        q, r = torch.linalg.qr(a.reshape(s[0] * s[1], s[2]), mode="reduced" if reduced else "complete")
+        q, r = householder_qr(a.reshape(s[0] * s[1], s[2]), complete=not reduced)
         return q.reshape(s[0], s[1], -1), r
 
     def _right_qr(self, a, reduced=True):

@@ -1,0 +1,180 @@
+// Householder QR on the device with LAPACK's conventions (zgeqr2 / zlarfg / zung2r).
+//
+// Why not cuSOLVER: the reference re-canonicalises the MPS at the start of every TDVP step
+// (tdvp.py:54) but keeps the environments it built before (tdvp.py:37-39, 122-145), so its results
+// depend on the SIGNS numpy/LAPACK's QR puts on the diagonal of R.  LAPACK's zlarfg chooses
+// beta = -sign(Re alpha) * ||(alpha, x)||; cuSOLVER's geqrf chooses differently, which changes the
+// evolved populations at the 1e-4 level.  Being a drop-in therefore needs this exact convention.
+//
+// One CTA per matrix (the matrices are MPS tensors: at most 2*chi x chi), column-major complex128
+// in global memory (L2 resident).  Cost is O(m n^2) on one SM: ~5 ms at 512 x 256, a few per cent
+// of a chi = 256 sweep.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "qca_common.cuh"
+
+namespace qca {
+
+constexpr int kQrThreads = 1024;
+
+struct cplx { double x, y; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return {a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x}; }  // conj(a) * b
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    // Smith's algorithm as in LAPACK's zladiv (robust scaling is not needed at these magnitudes)
+    if (fabs(b.y) < fabs(b.x)) {
+        const double e = b.y / b.x, f = b.x + b.y * e;
+        return {(a.x + a.y * e) / f, (a.y - a.x * e) / f};
+    }
+    const double e = b.x / b.y, f = b.y + b.x * e;
+    return {(a.y + a.x * e) / f, (-a.x + a.y * e) / f};
+}
+
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kQrThreads / 32; ++w) t += scratch[w];  // fixed order: deterministic
+    return t;
+}
+
+// A: m x n column-major (lda = m), overwritten with R (upper triangle) and the reflectors below
+// the diagonal; tau[k], k < min(m, n).
+__global__ void __launch_bounds__(kQrThreads) qr_factor_kernel(cplx* __restrict__ a, int m, int n, cplx* __restrict__ tau) {
+    extern __shared__ double smem[];
+    cplx* v = reinterpret_cast<cplx*>(smem);           // current reflector, m entries
+    double* scratch = smem + 2 * (size_t)m;             // 32 doubles
+    __shared__ cplx s_tau;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kQrThreads / 32;
+    const int kmax = m < n ? m : n;
+    for (int k = 0; k < kmax; ++k) {
+        cplx* col = a + (size_t)k * m;
+        // zlarfg: norm of the sub-diagonal part
+        double part = 0.0;
+        for (int i = k + 1 + tid; i < m; i += kQrThreads) part += col[i].x * col[i].x + col[i].y * col[i].y;
+        const double xnorm2 = block_sum(part, scratch);
+        if (tid == 0) {
+            const cplx alpha = col[k];
+            cplx t = {0.0, 0.0};
+            cplx scale = {0.0, 0.0};
+            double beta = alpha.x;
+            if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+                const double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2);
+                beta = -copysign(nrm, alpha.x);
+                t = {(beta - alpha.x) / beta, -alpha.y / beta};
+                scale = cdiv({1.0, 0.0}, {alpha.x - beta, alpha.y});
+                col[k] = {beta, 0.0};
+            }
+            s_tau = t;
+            tau[k] = t;
+            v[k] = {1.0, 0.0};
+            scratch[32] = scale.x; scratch[33] = scale.y;
+        }
+        __syncthreads();
+        const cplx t = s_tau;
+        const cplx scale = {scratch[32], scratch[33]};
+        const bool identity = (t.x == 0.0 && t.y == 0.0);
+        for (int i = k + 1 + tid; i < m; i += kQrThreads) {
+            cplx x = col[i];
+            if (!identity) x = cmul(scale, x);
+            col[i] = x;
+            v[i] = x;
+        }
+        __syncthreads();
+        if (!identity) {
+            // apply H^H = I - conj(tau) v v^H to the trailing columns: one warp per column
+            const cplx tc = {t.x, -t.y};
+            for (int j = k + 1 + warp; j < n; j += nwarps) {
+                cplx* c = a + (size_t)j * m;
+                cplx w = {0.0, 0.0};
+                for (int i = k + lane; i < m; i += 32) {
+                    const cplx p = cmulc(v[i], c[i]);
+                    w.x += p.x; w.y += p.y;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
+                    w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+                }
+                const cplx f = cmul(tc, w);
+                for (int i = k + lane; i < m; i += 32) {
+                    const cplx p = cmul(v[i], f);
+                    c[i].x -= p.x; c[i].y -= p.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Q (m x kq, column-major) = H_0 H_1 ... H_{kmax-1} applied to the first kq columns of the identity;
+// R (kr x n, column-major) = upper triangle of the factored A (kr = kq).
+__global__ void __launch_bounds__(kQrThreads) qr_form_kernel(const cplx* __restrict__ a, int m, int n,
+                                                              const cplx* __restrict__ tau, cplx* __restrict__ q,
+                                                              int kq, cplx* __restrict__ r) {
+    extern __shared__ double smem[];
+    cplx* v = reinterpret_cast<cplx*>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kQrThreads / 32;
+    const int kmax = m < n ? m : n;
+    for (size_t idx = tid; idx < (size_t)kq * n; idx += kQrThreads) {
+        const int i = (int)(idx % kq), j = (int)(idx / kq);
+        r[idx] = (i <= j && i < kmax) ? a[(size_t)j * m + i] : cplx{0.0, 0.0};
+    }
+    for (size_t idx = tid; idx < (size_t)m * kq; idx += kQrThreads) {
+        const int i = (int)(idx % m), j = (int)(idx / m);
+        q[idx] = (i == j) ? cplx{1.0, 0.0} : cplx{0.0, 0.0};
+    }
+    __syncthreads();
+    for (int k = kmax - 1; k >= 0; --k) {
+        const cplx t = tau[k];
+        for (int i = k + tid; i < m; i += kQrThreads) v[i] = (i == k) ? cplx{1.0, 0.0} : a[(size_t)k * m + i];
+        __syncthreads();
+        if (!(t.x == 0.0 && t.y == 0.0)) {
+            // columns j < k of Q are still unit vectors e_j with zero rows >= k: H_k leaves them alone
+            for (int j = k + warp; j < kq; j += nwarps) {
+                cplx* c = q + (size_t)j * m;
+                cplx w = {0.0, 0.0};
+                for (int i = k + lane; i < m; i += 32) {
+                    const cplx p = cmulc(v[i], c[i]);
+                    w.x += p.x; w.y += p.y;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
+                    w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+                }
+                const cplx f = cmul(t, w);
+                for (int i = k + lane; i < m; i += 32) {
+                    const cplx p = cmul(v[i], f);
+                    c[i].x -= p.x; c[i].y -= p.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace qca
+
+extern "C" {
+
+int32_t qca_qr_householder(void* a, int32_t m, int32_t n, void* tau, void* q, int32_t kq, void* r, void* stream) {
+    QCA_REQUIRE(a && tau && q && r, QCA_ERR_ARG, "NULL argument");
+    QCA_REQUIRE(m >= 1 && n >= 1 && m <= 8192, QCA_ERR_ARG, "matrix %d x %d out of range", m, n);
+    const int kmax = m < n ? m : n;
+    QCA_REQUIRE(kq == kmax || kq == m, QCA_ERR_ARG, "kq must be min(m,n) (reduced) or m (complete)");
+    const size_t smem = (2 * (size_t)m + 40) * sizeof(double);
+    cudaStream_t s = (cudaStream_t)stream;
+    QCA_CUDA(cudaFuncSetAttribute(qca::qr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCA_CUDA(cudaFuncSetAttribute(qca::qr_form_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qca::qr_factor_kernel<<<1, qca::kQrThreads, smem, s>>>((qca::cplx*)a, m, n, (qca::cplx*)tau);
+    QCA_CUDA(cudaGetLastError());
+    qca::qr_form_kernel<<<1, qca::kQrThreads, smem, s>>>((const qca::cplx*)a, m, n, (const qca::cplx*)tau,
+                                                       (qca::cplx*)q, kq, (qca::cplx*)r);
+    QCA_CUDA(cudaGetLastError());
+    return QCA_OK;
+}
+
+}  // extern "C"

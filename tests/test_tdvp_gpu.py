@@ -96,3 +96,28 @@ def test_tdvp_rejects_unsupported_algorithm():
     with pytest.raises(NotImplementedError):
         qca_b200.TDVP(qca_b200.states.make("single", rules), qca_b200.MPO.hamiltonian_from_rules(rules),
                       qca_b200.Args(rules=rules, algorithm="a1tdvp"))
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 1), (2, 2), (4, 2), (2, 4), (16, 8), (8, 16), (64, 32), (512, 256), (33, 7)])
+@pytest.mark.parametrize("complete", [False, True])
+def test_householder_qr_is_numpy_qr(m, n, complete):
+    """Same factors -- including the signs of R's diagonal -- as numpy.linalg.qr (LAPACK)."""
+    import torch
+    from qca_b200.linalg import householder_qr
+    rng = np.random.default_rng(m * 1000 + n)
+    mat = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    cases = [mat]
+    iso = np.linalg.qr(rng.standard_normal((max(m, n), max(m, n))) + 1j * rng.standard_normal((max(m, n), max(m, n))))[0][:m, :n]
+    cases.append(np.ascontiguousarray(iso))          # already orthonormal columns/rows: R = diag(+-1)
+    if n > 1:
+        deficient = mat.copy(); deficient[:, 1] = 0.0  # a zero column (tau = 0 branch of zlarfg)
+        cases.append(deficient)
+    for a in cases:
+        q_np, r_np = np.linalg.qr(a, mode="complete" if complete else "reduced")
+        q, r = householder_qr(torch.as_tensor(a, device="cuda"), complete=complete)
+        q, r = q.cpu().numpy(), r.cpu().numpy()
+        assert q.shape == q_np.shape and r.shape == r_np.shape
+        assert np.abs(r - r_np).max() < 1e-12 * max(1.0, np.abs(r_np).max())
+        assert np.abs(q @ r - a).max() < 1e-12
+        # columns of Q beyond the rank are a completion LAPACK fixes by the same reflectors
+        assert np.abs(q - q_np).max() < 1e-11
