@@ -136,6 +136,20 @@ def timestep(h: np.ndarray, psi: np.ndarray, delta: float) -> np.ndarray:
     return np.tensordot(psi, base.calculate_U(h, delta), (0, 0))
 
 
+def svd_with_random_phases(seed: int):
+    """An SVD as valid as LAPACK's: U diag(ph), s, diag(ph)^* Vh with random unit phases."""
+    rng = np.random.default_rng(seed)
+
+    def svd(a, full_matrices=False):
+        u, s, vh = np.linalg.svd(a, full_matrices=full_matrices)
+        ph = np.exp(2j * np.pi * rng.random(len(s)))
+        u, vh = u.copy(), vh.copy()
+        u[:, :len(s)] *= ph
+        vh[:len(s), :] *= ph.conj()[:, None]
+        return u, s, vh
+    return svd
+
+
 def merge_w(w0, w1):
     """MPO.merge_mpo_tensor_pair / tdvp.py:281-284."""
     w = np.einsum("abwm,cdmv->acbdwv", w0, w1)
@@ -147,8 +161,16 @@ class TDVPOracle:
     """algorithms/tdvp.py:9-146 for algorithm in {'1tdvp', '2tdvp'}."""
 
     def __init__(self, mps: list, wlist: list, algorithm: str, step_size: float, max_bond_dim: int,
-                 svd_epsilon: float):
+                 svd_epsilon: float, consistent: bool = False, svd=np.linalg.svd):
+        """consistent=False restates the reference literally.  The reference re-canonicalises the
+        MPS at the start of every step (tdvp.py:54) and inside every measurement (mps.py:110) but
+        keeps the right environments it built earlier; they are then stale by the gauge signs of
+        the QR, and the 2TDVP result depends on the (arbitrary) phases of the SVD's singular
+        vectors at the 1e-4 level (tests/golden/*: ``gauge_spread``).  consistent=True rebuilds the
+        right environments after the re-canonicalisation -- the gauge-invariant algorithm the B200
+        2TDVP implements.  `svd` lets the tests inject an equivalent SVD with other phases."""
         self.a, self.w = mps, wlist
+        self.consistent, self.svd = consistent, svd
         self.algorithm, self.dt, self.chi, self.eps = algorithm, step_size, max_bond_dim, svd_epsilon
         n = len(mps)
         make_site_canonical(self.a, n - 1)  # tdvp.py:23-26
@@ -180,7 +202,7 @@ class TDVPOracle:
         theta = np.einsum("alm,bmr->ablr", al, ar).reshape(4, al.shape[1], ar.shape[2])
         new = self._evolve_tensor(theta, self._left(i - 1), self._right(j + 1), merge_w(self.w[i], self.w[j]), self.dt / 2)
         mat = new.reshape(2, 2, al.shape[1], ar.shape[2]).transpose(0, 2, 1, 3).reshape(2 * al.shape[1], 2 * ar.shape[2])
-        u, s, vh = np.linalg.svd(mat, full_matrices=False)
+        u, s, vh = self.svd(mat, full_matrices=False)
         cap = min(self.chi, len(s))
         keep = next((k for k in range(len(s)) if np.linalg.norm(s[k:]) < self.eps), cap)
         keep = min(keep, cap)
@@ -193,6 +215,9 @@ class TDVPOracle:
         """do_time_step, tdvp.py:50-63."""
         n = len(self.a)
         make_site_canonical(self.a, 0)
+        if self.consistent:
+            for site in reversed(range(1, n)):
+                self.right[site] = grow_right(self._right(site + 1), self.a[site], self.w[site])
         if self.algorithm == "2tdvp":
             for site in range(n - 1):  # tdvp.py:107-125
                 ul, s, vr = self._two_site(site, site + 1)
@@ -239,10 +264,12 @@ class TDVPOracle:
 
 
 def run_tdvp(state: str, ncells: int, distance: int, lo: int, hi: int, algorithm: str, step_size: float,
-             num_steps: int, plot_step_interval: int, max_bond_dim: int, svd_epsilon: float):
+             num_steps: int, plot_step_interval: int, max_bond_dim: int, svd_epsilon: float,
+             consistent: bool = False, svd=np.linalg.svd):
     """quantum_game.py:82-119 for a TDVP algorithm: measure every plot_step_interval steps."""
     mps = product_mps(base.initial_plist(state, ncells, distance))
-    algo = TDVPOracle(mps, base.mpo_tensors(ncells, distance, lo, hi), algorithm, step_size, max_bond_dim, svd_epsilon)
+    algo = TDVPOracle(mps, base.mpo_tensors(ncells, distance, lo, hi), algorithm, step_size, max_bond_dim, svd_epsilon,
+                      consistent=consistent, svd=svd)
     pops, ents, bonds = [], [], []
     for step in range(num_steps):
         if step % plot_step_interval == 0:

@@ -13,6 +13,17 @@ to bond dimension ~32.  Here the MPS, the MPO and the environments live on the d
 * QR runs on the device with LAPACK's Householder conventions (csrc/qca_linalg.cu -- the
   reference's numbers depend on them), SVD / truncation on the device through torch.linalg.
 
+Gauge consistency (2tdvp).  The reference re-canonicalises the MPS at the start of every step
+(tdvp.py:54) and inside every measurement (mps.py:110) but keeps the right environments it built
+before; they are then stale by the QR's gauge signs and its 2TDVP numbers depend on the arbitrary
+phases of the singular vectors np.linalg.svd returns: fed an equivalent SVD with other phases, the
+unmodified reference moves its own populations by up to 4e-4 and entropies by 7e-3
+(``gauge_spread_*`` in tests/golden/tdvp2_*.npz).  No implementation on another SVD can reproduce
+those digits, so 2tdvp here is the gauge-INVARIANT algorithm: whenever the gauge of the tensors has
+changed (construction, measurement, a new psi) the right environments are rebuilt.  It agrees with
+the reference within the reference's own spread and with the oracle's ``consistent=True`` variant
+to 1e-8.  1tdvp involves no SVD and mirrors the reference literally (1e-8 against its fixtures).
+
 Index conventions are the reference's: ``A[p,l,r]``, ``W[a,b,wl,wr]``, environments ``L[x,w,y]`` /
 ``R[u,w,v]`` with x/u on the ket side.  Same sweep order, same truncation rule
 (tdvp.py:289-296), same gauge handling (mps.py:146-192) as the reference.
@@ -73,6 +84,7 @@ class TDVP(Algorithm):
             self._canonicalize(site - 1)
             self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
         self.heff_applications = 0
+        self._gauge_dirty = False  # tensors and right environments are in the same gauge right now
 
     # -- Algorithm interface ----------------------------------------------------------------
     @property
@@ -83,6 +95,7 @@ class TDVP(Algorithm):
     def psi(self, value: MPS) -> None:
         torch = _torch()
         self._A = [torch.as_tensor(np.ascontiguousarray(a), dtype=self.ct, device=self.dev) for a in value.A]
+        self._gauge_dirty = True
 
     def measure(self, population, d_population, single_site_entropy, bond_dims) -> None:
         """MPS.measure (mps.py:100-140): sweep the orthogonality centre through the chain on the
@@ -93,6 +106,7 @@ class TDVP(Algorithm):
         bond_dims[:n] = [a.shape[1] for a in self._A]
         bond_dims[n] = self._A[-1].shape[2]
         self._canonicalize(0)
+        self._gauge_dirty = True
         rhos = []
         for site in range(n):
             if site > 0:
@@ -109,11 +123,18 @@ class TDVP(Algorithm):
 
     def do_time_step(self) -> None:
         """tdvp.py:50-63."""
-        self._canonicalize(0)
         if self.args.algorithm == "2tdvp":
+            if self._gauge_dirty:
+                # (after a completed step the MPS already is right-canonical with centre 0 and the
+                #  right environments match it: re-canonicalising would be a pure gauge change)
+                self._canonicalize(0)
+                for site in reversed(range(1, len(self._A))):
+                    self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+                self._gauge_dirty = False
             self._sweep_right_two_site()
             self._sweep_left_two_site()
         else:
+            self._canonicalize(0)
             self._sweep_right_one_site()
             self._sweep_left_one_site()
 

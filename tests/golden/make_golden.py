@@ -94,31 +94,62 @@ def child(spec: dict, ref: str) -> None:
 
     import states
     from algorithms import Exact, TDVP
-    if spec["state"] == "single":  # default argument is frozen at import: states.py:34
-        psi0 = states.single(position=int(n / 2))
-    else:
-        psi0 = getattr(states, spec["state"])()
+    def make_state():
+        if spec["state"] == "single":  # default argument is frozen at import: states.py:34
+            return states.single(position=int(n / 2))
+        return getattr(states, spec["state"])()
+
+    psi0 = make_state()
     out["psi0"] = psi0.as_vector()
     # quantum_game.py:70-73
     if args.algorithm == "exact":
         args.step_size = args.step_size * args.plot_step_interval
     out["effective_step_size"] = args.step_size
     out["plot_step_interval"] = args.plot_step_interval
-    algo = (Exact if args.algorithm == "exact" else TDVP)(psi_0=psi0, H=H, args=args)
-    pop = np.zeros([args.plot_steps, n]); dpop = np.zeros_like(pop); sse = np.zeros_like(pop)
-    bond = np.zeros([args.plot_steps, n + 1])
-    # quantum_game.py:82-119 minus csv/npz/plot side effects
-    for step in range(args.num_steps):
-        if step % args.plot_step_interval == 0:
-            k = step // args.plot_step_interval
-            algo.measure(population=pop[k, :], d_population=dpop[k, :],
-                         single_site_entropy=sse[k, :], bond_dims=bond[k, :])
-            if args.algorithm == "exact":
+    def run_reference():
+        algo = (Exact if args.algorithm == "exact" else TDVP)(psi_0=make_state(), H=H, args=args)
+        pop = np.zeros([args.plot_steps, n]); dpop = np.zeros_like(pop); sse = np.zeros_like(pop)
+        bond = np.zeros([args.plot_steps, n + 1])
+        # quantum_game.py:82-119 minus csv/npz/plot side effects
+        for step in range(args.num_steps):
+            if step % args.plot_step_interval == 0:
+                k = step // args.plot_step_interval
+                algo.measure(population=pop[k, :], d_population=dpop[k, :],
+                             single_site_entropy=sse[k, :], bond_dims=bond[k, :])
+                if args.algorithm == "exact":
+                    algo.do_time_step()
+            if args.algorithm != "exact":
                 algo.do_time_step()
-        if args.algorithm != "exact":
-            algo.do_time_step()
+        return pop, dpop, sse, bond, (algo.psi.as_vector() if args.algorithm != "exact" else algo._psi)
+
+    pop, dpop, sse, bond, psi_final = run_reference()
     out.update(population=pop, d_population=dpop, single_site_entropy=sse, bond_dims=bond)
-    out["psi_final"] = algo.psi.as_vector() if args.algorithm != "exact" else algo._psi
+    out["psi_final"] = psi_final
+    if args.algorithm == "2tdvp":
+        # The reference's 2TDVP depends on the arbitrary phases of the singular vectors np.linalg.svd
+        # returns (stale environments after re-canonicalisation).  Record how far the UNMODIFIED
+        # reference moves when the SVD is replaced by an equivalent one with random phases.
+        stock = np.linalg.svd
+        spread_pop, spread_sse = 0.0, 0.0
+        for seed in (1, 2, 3, 4):
+            rng = np.random.default_rng(seed)
+
+            def svd(a, full_matrices=True, **kw):
+                u, s, vh = stock(a, full_matrices=full_matrices, **kw)
+                ph = np.exp(2j * np.pi * rng.random(len(s)))
+                u, vh = u.copy(), vh.copy()
+                u[:, :len(s)] *= ph
+                vh[:len(s), :] *= ph.conj()[:, None]
+                return u, s, vh
+            np.linalg.svd = svd
+            try:
+                p2, _, s2, _, _ = run_reference()
+            finally:
+                np.linalg.svd = stock
+            spread_pop = max(spread_pop, np.abs(p2 - pop).max())
+            spread_sse = max(spread_sse, np.abs(s2 - sse).max())
+        out["gauge_spread_population"] = spread_pop
+        out["gauge_spread_entropy"] = spread_sse
     if spec["kind"] == "exact":
         from algorithms import Algorithm
         out["classical"] = Algorithm.classical_evolution(dpop[0, :], args.rules, args.plot_steps)
