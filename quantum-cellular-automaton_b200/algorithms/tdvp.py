@@ -36,7 +36,7 @@ import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
-from ..linalg import householder_qr
+from ..linalg import gram_svd, householder_qr
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
@@ -81,7 +81,11 @@ class TDVP(Algorithm):
         self._target_bond_dims = list(self._max_bond_dims)
         self._one = torch.ones((1, 1, 1), dtype=self.ct, device=self.dev)
         for site in reversed(range(1, n)):  # tdvp.py:37-39
-            self._canonicalize(site - 1)
+            if args.algorithm == "1tdvp":
+                # literal: the reference moves the centre to site-1 with a full O(N) sweep each time
+                self._canonicalize(site - 1)
+            # (2tdvp is gauge invariant: every tensor right of site 0 already is right-orthonormal,
+            #  so the O(N^2) re-canonicalisations of the reference would only change gauge signs)
             self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
         self.heff_applications = 0
         self._gauge_dirty = False  # tensors and right environments are in the same gauge right now
@@ -272,12 +276,15 @@ class TDVP(Algorithm):
         new = self._expm_apply(lambda v: self._apply_two_site(left, right, w1, w2, v), theta, self.args.step_size / 2)
         dl, dr = al.shape[1], ar.shape[2]
         mat = new.permute(0, 2, 1, 3).reshape(2 * dl, 2 * dr)
-        u, s, vh = torch.linalg.svd(mat, full_matrices=False)
-        # tdvp.py:290-292: first k with ||s[k:]|| < epsilon, capped by max_bond_dim
-        tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]))
-        below = (tail < self.args.svd_epsilon).nonzero()
-        cap = min(self.args.max_bond_dim, s.shape[0])
-        keep = min(int(below[0, 0]) if below.numel() else cap, cap)
+        # singular values that truncation can never keep are not resolved one by one: with
+        # stop_below = eps / (4 sqrt(n)) the unresolved rest has norm < eps, so the first index whose
+        # tail norm is under eps (tdvp.py:290-292) always lies inside the resolved part
+        eps = self.args.svd_epsilon
+        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))))
+        tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
+        below = (tail < eps).nonzero()
+        cap = min(self.args.max_bond_dim, 2 * min(dl, dr))
+        keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
         ul = u.reshape(2, dl, -1)[:, :, :keep]
         vr = vh.reshape(-1, 2, dr).permute(1, 0, 2)[:, :keep, :]
         sk = s[:keep] / torch.linalg.vector_norm(s[:keep])

@@ -21,12 +21,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int32_t validate_rule(const qca_rule_t* r) {
+int32_t validate_rule(const qca_rule_t* r, int max_cells) {
     QCA_REQUIRE(r != nullptr, QCA_ERR_ARG, "rule is NULL");
     QCA_REQUIRE(r->ncells >= 1, QCA_ERR_ARG, "ncells must be >= 1 (got %d)", r->ncells);
     QCA_REQUIRE(r->distance >= 1, QCA_ERR_ARG, "distance must be >= 1 (got %d)", r->distance);
     QCA_REQUIRE(r->distance <= 7, QCA_ERR_UNSUPPORTED, "distance > 7 not supported (got %d)", r->distance);
-    QCA_REQUIRE(r->ncells <= 40, QCA_ERR_UNSUPPORTED, "ncells > 40 not supported (got %d)", r->ncells);
+    QCA_REQUIRE(r->ncells <= max_cells, QCA_ERR_UNSUPPORTED, "ncells > %d not supported here (got %d)", max_cells, r->ncells);
     QCA_REQUIRE(r->act_lo >= 0 && r->act_hi >= r->act_lo, QCA_ERR_ARG,
                 "activation interval [%d,%d) is not a range", r->act_lo, r->act_hi);
     return QCA_OK;
@@ -192,7 +192,7 @@ const char* qca_version(void) { return "qca_b200 0.1 (sm_100a)"; }
 const char* qca_last_error(void) { return qca::g_error; }
 
 int32_t qca_spectral_bound(const qca_rule_t* rule, double* bound) {
-    QCA_CHECK(qca::validate_rule(rule));
+    QCA_CHECK(qca::validate_rule(rule, 1 << 20));  // chains of any TDVP length: the DP is O(ncells)
     QCA_REQUIRE(bound != nullptr, QCA_ERR_ARG, "bound is NULL");
     *bound = qca::spectral_bound(*rule);
     return QCA_OK;

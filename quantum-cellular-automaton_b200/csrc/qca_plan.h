@@ -12,7 +12,8 @@ constexpr int kTileBits = 13;
 // global accesses stay full cache lines.
 constexpr int kMinLowBits = 4;
 
-int32_t validate_rule(const qca_rule_t* r);
+// max_cells: 40 for the state-vector engine (index bits), unbounded for chain-level planning
+int32_t validate_rule(const qca_rule_t* r, int max_cells = 40);
 double spectral_bound(const qca_rule_t& r);
 int32_t chebyshev_plan(double z, double tol, std::vector<double>& a);
 void plan_passes(int local_bits, std::vector<qca_pass_t>& out);

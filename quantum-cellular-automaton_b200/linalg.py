@@ -23,3 +23,58 @@ def householder_qr(mat, complete: bool = False):
                                            C.c_void_p(q.data_ptr()), kq, C.c_void_p(r.data_ptr()),
                                            C.c_void_p(stream)))
     return q.T, r.T
+
+
+def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels: int = 6):
+    """Thin SVD of a complex128 CUDA matrix from Hermitian eigendecompositions of Gram matrices.
+
+    cuSOLVER's SVD of a 512 x 512 complex128 matrix takes 60-130 ms on a B200 and was 88 % of a
+    chi = 256 2TDVP sweep; ``eigh`` of the Gram matrix takes 6.5 ms.  One Gram step resolves
+    singular values only down to ~1e-8 of the largest, so the spectrum is peeled in levels: the
+    eigenvectors with sigma >= level_ratio * (largest of the level) are accepted (relative error at
+    most eps / level_ratio^2 = 1e-10, at the bottom of a level), the matrix is deflated onto the
+    remaining right-singular subspace and the procedure repeats there, where the small singular
+    values are the large ones.  Absolute accuracy is eps * sigma_1 / level_ratio = 1e-13 sigma_1,
+    the same order as LAPACK's backward-stable SVD.
+
+    stop_below: singular values below it are not resolved individually (2TDVP never keeps them:
+    tdvp.py:290-292 truncates where the tail norm drops under svd_epsilon); they are returned only
+    through `rest_norm`, the Frobenius norm of the unresolved part.
+
+    Returns (u, s, vh, rest_norm): s descending, u[:, i] = mat @ v_i / s_i, mat ~= u diag(s) vh
+    up to rest_norm.
+    """
+    import torch
+    m, n = mat.shape
+    if m < n:  # work on the side with the smaller Gram matrix
+        u, s, vh, rest = gram_svd(mat.conj().T, stop_below, level_ratio, max_levels)
+        return vh.conj().T, s, u.conj().T, rest
+    basis = None          # right-singular subspace still to be resolved (n x k), None = everything
+    us, ss, vs = [], [], []
+    rest_norm = torch.zeros((), dtype=torch.float64, device=mat.device)
+    for level in range(max_levels):
+        work = mat if basis is None else mat @ basis
+        gram = work.conj().T @ work
+        gram = 0.5 * (gram + gram.conj().T)
+        lam, vec = torch.linalg.eigh(gram)
+        lam, vec = lam.flip(0).clamp_min(0.0), vec.flip(1)
+        sig = torch.sqrt(lam)
+        top = float(sig[0])                                   # the one host sync of a level
+        if level > 0 and top < stop_below:
+            rest_norm = torch.linalg.vector_norm(work)
+            break
+        last = level == max_levels - 1
+        keep = sig.shape[0] if (last or top == 0.0) else int((sig >= level_ratio * top).sum())
+        v_here = vec if basis is None else basis @ vec
+        b = work @ vec[:, :keep]
+        s_here = torch.linalg.vector_norm(b, dim=0)           # more accurate than sqrt(lam) at the level's bottom
+        safe = torch.where(s_here > 0, s_here, torch.ones_like(s_here))
+        us.append(b / safe)
+        ss.append(s_here)
+        vs.append(v_here[:, :keep])
+        if keep == sig.shape[0]:
+            break
+        basis = v_here[:, keep:]
+    u, s, v = torch.cat(us, dim=1), torch.cat(ss), torch.cat(vs, dim=1)
+    order = torch.argsort(s, descending=True, stable=True)    # levels are ordered; ties inside noise only
+    return u[:, order], s[order], v[:, order].conj().T, rest_norm

@@ -1,0 +1,47 @@
+"""gram_svd (multi-level Gram-matrix SVD used by the 2TDVP split) against numpy's SVD.  The routine is
+pure tensor algebra, so its numerics are checked on CPU tensors here and on the device in
+tests/test_tdvp_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from qca_b200.linalg import gram_svd
+
+
+def matrix_with_spectrum(m, n, sigma, rng):
+    k = min(m, n)
+    u = np.linalg.qr(rng.standard_normal((m, k)) + 1j * rng.standard_normal((m, k)))[0]
+    v = np.linalg.qr(rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k)))[0]
+    return (u * sigma) @ v.conj().T
+
+
+@pytest.mark.parametrize("m,n,decay", [(64, 64, 30.0), (128, 64, 36.0), (64, 128, 20.0), (256, 256, 5.0), (2, 8, 1.0), (1, 1, 0.0)])
+def test_gram_svd_matches_lapack(m, n, decay):
+    rng = np.random.default_rng(m + n)
+    k = min(m, n)
+    sigma = np.exp(-np.arange(k) * decay / k)
+    a = matrix_with_spectrum(m, n, sigma, rng)
+    u, s, vh, rest = gram_svd(torch.as_tensor(a))
+    u, s, vh = u.resolve_conj().numpy(), s.numpy(), vh.resolve_conj().numpy()
+    assert float(rest) == 0.0 and len(s) == k
+    s_np = np.linalg.svd(a, compute_uv=False)
+    assert np.abs(s - s_np).max() < 1e-13                       # backward-stable accuracy, like LAPACK
+    big = s_np > 1e-9
+    assert (np.abs(s[big] - s_np[big]) / s_np[big]).max() < 1e-7
+    assert np.abs((u * s) @ vh - a).max() < 1e-13
+    assert np.abs(u[:, big].conj().T @ u[:, big] - np.eye(big.sum())).max() < 1e-4   # worst in directions of weight < 1e-17
+    assert np.abs(vh[big] @ vh[big].conj().T - np.eye(big.sum())).max() < 1e-4
+    well = s_np > 1e-5
+    assert np.abs(u[:, well].conj().T @ u[:, well] - np.eye(well.sum())).max() < 1e-9
+
+
+def test_gram_svd_stops_below_the_truncation_floor():
+    rng = np.random.default_rng(1)
+    sigma = np.exp(-np.arange(128) * 36.0 / 128)
+    a = matrix_with_spectrum(128, 128, sigma, rng)
+    u, s, vh, rest = gram_svd(torch.as_tensor(a), stop_below=1e-6)
+    s = s.numpy()
+    r = len(s)
+    assert r < 128 and s.min() < 1e-3      # stopped early, but resolved well below any 2TDVP cut-off
+    assert abs(float(rest) - np.sqrt((sigma[r:] ** 2).sum())) < 1e-12
+    assert np.abs(s - sigma[:r]).max() < 1e-13

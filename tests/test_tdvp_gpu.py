@@ -152,3 +152,17 @@ def test_householder_qr_is_numpy_qr(m, n, complete):
         assert np.abs(q @ r - a).max() < 1e-12
         # columns of Q beyond the rank are a completion LAPACK fixes by the same reflectors
         assert np.abs(q - q_np).max() < 1e-11
+
+
+def test_gram_svd_on_device_matches_lapack():
+    import torch
+    from qca_b200.linalg import gram_svd
+    rng = np.random.default_rng(3)
+    k = 192
+    u0 = np.linalg.qr(rng.standard_normal((256, k)) + 1j * rng.standard_normal((256, k)))[0]
+    v0 = np.linalg.qr(rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k)))[0]
+    sigma = np.exp(-np.arange(k) * 30.0 / k)
+    a = (u0 * sigma) @ v0.conj().T
+    u, s, vh, rest = gram_svd(torch.as_tensor(a, device="cuda"))
+    u, s, vh = u.cpu().resolve_conj().numpy(), s.cpu().numpy(), vh.cpu().resolve_conj().numpy()
+    assert np.abs(s - sigma).max() < 1e-13 and np.abs((u * s) @ vh - a).max() < 1e-13
