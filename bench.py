@@ -44,6 +44,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-num-cells", type=int, default=12, help="chain length of the bounded CPU sample")
+    ap.add_argument("--no-tdvp", action="store_true", help="skip the 2TDVP chi=256 leg")
+    ap.add_argument("--tdvp-cells", type=int, default=64)
+    ap.add_argument("--tdvp-chi", type=int, default=256)
+    ap.add_argument("--tdvp-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -297,6 +301,12 @@ def b200_arm(args) -> None:
         del host
 
     cpu = None if (args.no_cpu_baseline or world > 1 or rank != 0) else cpu_reference_run(args, 200, 5)
+    tdvp = None
+    if not args.no_tdvp and world == 1:
+        try:
+            tdvp = tdvp_leg(args, local_rank)
+        except Exception as exc:  # the exact leg's numbers stand on their own
+            tdvp = {"error": repr(exc)}
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -306,11 +316,79 @@ def b200_arm(args) -> None:
                                                      "sharding": f"top {world.bit_length() - 1} qubits over {world} ranks, "
                                                                  "partner reads over NVLink peer memory" if world > 1 else "none"}),
             "roofline": roofline, "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": e2e, "gpu_launches": int(st["kernel_launches"]) * world, "clocks": clocks}
+            "e2e": e2e, "gpu_launches": int(st["kernel_launches"]) * world, "clocks": clocks, "tdvp": tdvp}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# second half of the BASELINE metric: 2TDVP sweeps/s at chi = 256 (single GPU)
+# ---------------------------------------------------------------------------------------------
+def tdvp_leg(args, device: int) -> dict:
+    """configs[4]: 2tdvp, --num-cells 64, bond cap chi = 256.  A product state only reaches chi = 256
+    after thousands of steps, so (north_star: "synthetic initial states of the named sizes") the MPS
+    is a seeded random one whose bonds are already at the cap, with the SVD cut-off low enough to
+    keep them there.  One time step = one right plus one left sweep (tdvp.py:50-63)."""
+    import numpy as np
+    import torch
+    import qca_b200
+    n, chi = args.tdvp_cells, args.tdvp_chi
+    rules = qca_b200.Rules(n, range(1, 2), 1)
+    targs = qca_b200.Args(rules=rules, step_size=0.005, algorithm="2tdvp", max_bond_dim=chi, svd_epsilon=1e-14)
+    rng = np.random.default_rng(0)
+    dims = [min(2 ** i, 2 ** (n - i), chi) for i in range(n + 1)]
+    mps = qca_b200.MPS([(rng.standard_normal((2, dims[i], dims[i + 1])) + 1j * rng.standard_normal((2, dims[i], dims[i + 1])))
+                        / np.sqrt(2 * dims[i]) for i in range(n)])
+    h2d = sum(a.nbytes for a in mps.A)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    algo = qca_b200.TDVP(mps, qca_b200.MPO.hamiltonian_from_rules(rules), targs, device=device)
+    torch.cuda.synchronize()
+    init_s = time.perf_counter() - t0
+    pop, dpop, sse, bond = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n + 1)
+    for _ in range(max(args.warmup, 1)):
+        algo.do_time_step()
+    torch.cuda.synchronize()
+    algo.heff_applications, algo.heff_flops = 0, 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.tdvp_steps):
+        algo.do_time_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    flops, napply = algo.heff_flops, algo.heff_applications
+    # through the plug-in API with a measurement every step (D2H of the N density matrices)
+    t1 = time.perf_counter()
+    for _ in range(args.tdvp_steps):
+        algo.measure(pop, dpop, sse, bond)
+        algo.do_time_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    # denominator measured here: cuBLAS DGEMM (the box has no measured FP64 figure in MEASURED_PEAKS.json)
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b); torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(); torch.matmul(a, b); torch.matmul(a, b); g1.record(); torch.cuda.synchronize()
+    dgemm_tflops = 2 * 2.0 * 8192 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
+    del a, b
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"metric": "2TDVP sweeps/s at chi=256", "value": 2 * args.tdvp_steps / (ms * 1e-3), "unit": "sweeps/s",
+            "ms_per_time_step": ms / args.tdvp_steps, "steps": args.tdvp_steps, "init_s": init_s,
+            "config": {"workload": f"2tdvp, --num-cells {n}, --max-bond-dim {chi}, distance 1, interval [1,2), step 0.005, "
+                                   "seeded random MPS at the bond cap, svd_epsilon 1e-14", "max_bond": int(max(dims))},
+            "heff_applications_per_step": napply / args.tdvp_steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / dgemm_tflops, "traffic": None,
+                         "note": "FP64 flops of the H_eff contractions (8 per complex MAC, dense W) / the WHOLE step time "
+                                 "(Lanczos vector work, SVD and QR included); peak = cuBLAS DGEMM 8192^3 measured in this run "
+                                 "(nominal B200 FP64 tensor peak: 40 TFLOP/s)"},
+            "e2e": {"value": 2 * args.tdvp_steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 64 * n, "h2d_bytes_once": h2d,
+                    "api": "TDVP.measure + TDVP.do_time_step (state resident on the device between steps, as in the reference's loop)"}}
 
 
 def main():

@@ -88,6 +88,7 @@ class TDVP(Algorithm):
             #  so the O(N^2) re-canonicalisations of the reference would only change gauge signs)
             self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
         self.heff_applications = 0
+        self.heff_flops = 0.0      # real FP64 operations of the H_eff contractions (8 per complex MAC)
         self._gauge_dirty = False  # tensors and right environments are in the same gauge right now
 
     # -- Algorithm interface ----------------------------------------------------------------
@@ -208,6 +209,8 @@ class TDVP(Algorithm):
     def _apply_one_site(self, left, right, w, psi):
         torch = _torch()
         self.heff_applications += 1
+        dl, dr, wl, wr = left.shape[0], right.shape[0], left.shape[1], right.shape[1]
+        self.heff_flops += 8.0 * (2 * wl * dl * dl * dr + 4 * wl * wr * dl * dr + 2 * wr * dl * dr * dr)
         t = torch.einsum("xwy,axu->awyu", left, psi)
         t = torch.einsum("abwm,awyu->bmyu", w, t)
         return torch.einsum("bmyu,umv->byv", t, right)
@@ -215,6 +218,9 @@ class TDVP(Algorithm):
     def _apply_two_site(self, left, right, w1, w2, theta):
         torch = _torch()
         self.heff_applications += 1
+        dl, dr, wl, wm, wr = left.shape[0], right.shape[0], left.shape[1], w1.shape[3], right.shape[1]
+        self.heff_flops += 8.0 * (4 * wl * dl * dl * dr + 8 * wl * wm * dl * dr + 8 * wm * wr * dl * dr
+                                  + 4 * wr * dl * dr * dr)
         t = torch.einsum("xwy,acxu->acwyu", left, theta)
         t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
         t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)
