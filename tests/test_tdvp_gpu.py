@@ -166,3 +166,22 @@ def test_gram_svd_on_device_matches_lapack():
     u, s, vh, rest = gram_svd(torch.as_tensor(a, device="cuda"))
     u, s, vh = u.cpu().resolve_conj().numpy(), s.cpu().numpy(), vh.cpu().resolve_conj().numpy()
     assert np.abs(s - sigma).max() < 1e-13 and np.abs((u * s) @ vh - a).max() < 1e-13
+
+
+@pytest.mark.parametrize("dx,w,du,g", [(1, 1, 1, 1), (3, 6, 5, 4), (16, 6, 16, 4), (64, 6, 64, 4), (70, 5, 33, 2),
+                                       (128, 14, 96, 4), (256, 6, 256, 4), (17, 6, 200, 2), (200, 6, 17, 2)])
+def test_dmma_contractions_match_einsum(dx, w, du, g):
+    """The two FP64 tensor-core contractions of H_eff against torch.einsum (cuBLAS)."""
+    import torch
+    from qca_b200.linalg import env_times_tensor, tensor_times_env
+    gen = torch.Generator(device="cuda").manual_seed(dx * 1000 + du)
+    def rnd(*shape):
+        return torch.randn(*shape, dtype=torch.complex128, device="cuda", generator=gen)
+    left, theta = rnd(dx, w, dx), rnd(g, dx, du)
+    got = env_times_tensor(left, theta)
+    want = torch.einsum("xwy,gxu->gwyu", left, theta)
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+    t, right = rnd(g, w, dx, du), rnd(du, w, du)
+    got = tensor_times_env(t, right)
+    want = torch.einsum("gnyu,unv->gyv", t, right)
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
