@@ -181,10 +181,13 @@ int32_t qca_qr_householder(void* a, int32_t m, int32_t n, void* tau, void* q, in
 /* Batched, segmented complex128 GEMM on the FP64 tensor cores (DMMA) for the effective-Hamiltonian
  * contractions (np.tensordot in tdvp.py:299-347):  C_g[m,n] = sum_{s<S} sum_{k<K} A_{g,s}[m,k] B_{g,s}[k,n].
  * DEVICE pointers, strides in complex128 elements: A at g*a_sg + s*a_ss + m*a_sm + k*a_sk (a_sm == 1 or
- * a_sk == 1), B at g*b_sg + s*b_ss + k*b_sk + n, C at g*c_sg + m*c_sm + n.  conj_a: use conj(A). */
+ * a_sk == 1), B at g*b_sg + s*b_ss + k*b_sk + n, C at g*c_sg + m*c_sm + n.  conj_a: use conj(A).
+ * nsplit > 1 splits the (s, k) reduction over nsplit CTAs per tile; split i writes its partial sum to
+ * c + i*c_ssplit and the caller adds the partials (fixed order: deterministic). */
 int32_t qca_zgemm_batched(const void* a, const void* b, void* c, int32_t M, int32_t N, int32_t K, int32_t S, int32_t G,
                           int64_t a_sg, int64_t a_ss, int64_t a_sm, int64_t a_sk, int64_t b_sg, int64_t b_ss,
-                          int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, void* stream);
+                          int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, int32_t nsplit, int64_t c_ssplit,
+                          void* stream);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The state is sharded over the top

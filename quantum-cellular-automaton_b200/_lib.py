@@ -90,7 +90,7 @@ SYMBOLS = {
     "qca_qr_householder": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
     "qca_zgemm_batched": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 9
-                          + [C.c_int32, C.c_void_p]),
+                          + [C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -36,10 +36,11 @@ import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
-from ..linalg import gram_svd, householder_qr
+from ..linalg import env_times_tensor, gram_svd, householder_qr, tensor_times_env
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
+DMMA_MIN_BOND = 16        # bonds from which the two heavy contractions run on the DMMA kernel
 KRYLOV_TOL = 1e-16
 
 
@@ -211,6 +212,10 @@ class TDVP(Algorithm):
         self.heff_applications += 1
         dl, dr, wl, wr = left.shape[0], right.shape[0], left.shape[1], right.shape[1]
         self.heff_flops += 8.0 * (2 * wl * dl * dl * dr + 4 * wl * wr * dl * dr + 2 * wr * dl * dr * dr)
+        if min(dl, dr) >= DMMA_MIN_BOND:   # FP64 tensor-core path (csrc/qca_zgemm.cu)
+            t = env_times_tensor(left, psi)
+            t = torch.einsum("abwm,awyu->bmyu", w, t)
+            return tensor_times_env(t, right)
         t = torch.einsum("xwy,axu->awyu", left, psi)
         t = torch.einsum("abwm,awyu->bmyu", w, t)
         return torch.einsum("bmyu,umv->byv", t, right)
@@ -221,6 +226,11 @@ class TDVP(Algorithm):
         dl, dr, wl, wm, wr = left.shape[0], right.shape[0], left.shape[1], w1.shape[3], right.shape[1]
         self.heff_flops += 8.0 * (4 * wl * dl * dl * dr + 8 * wl * wm * dl * dr + 8 * wm * wr * dl * dr
                                   + 4 * wr * dl * dr * dr)
+        if min(dl, dr) >= DMMA_MIN_BOND:   # FP64 tensor-core path (csrc/qca_zgemm.cu)
+            t = env_times_tensor(left, theta.reshape(4, dl, dr)).reshape(2, 2, wl, dl, dr)
+            t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
+            t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)
+            return tensor_times_env(t.reshape(4, wr, dl, dr), right).reshape(2, 2, dl, dr)
         t = torch.einsum("xwy,acxu->acwyu", left, theta)
         t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
         t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)

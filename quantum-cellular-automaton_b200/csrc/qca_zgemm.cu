@@ -40,6 +40,8 @@ struct ZgemmArgs {
     long long c_sg, c_sm;
     int M, N, K, S, G;
     int conj_a;   // use conj(A)
+    int nsplit;   // split-K: blockIdx.z = g * nsplit + split; partial sums go to c + split * c_ssplit
+    long long c_ssplit;
 };
 
 __device__ __forceinline__ void zg_cp_async16(void* smem, const void* gmem, bool valid) {
@@ -49,8 +51,8 @@ __device__ __forceinline__ void zg_cp_async16(void* smem, const void* gmem, bool
 }
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 template <bool A_MMAJOR>   // A_MMAJOR: A has k contiguous in global memory (a_sk == 1), staged as [m][k]
@@ -58,16 +60,19 @@ __global__ void __launch_bounds__(ZG_THREADS, 2) zgemm_dmma_kernel(const ZgemmAr
     extern __shared__ double2 zsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;          // warp grid 2 x 4
-    const int m0 = blockIdx.y * ZG_TM, n0 = blockIdx.x * ZG_TN, g = blockIdx.z;
+    const int m0 = blockIdx.y * ZG_TM, n0 = blockIdx.x * ZG_TN;
+    const int g = blockIdx.z / p.nsplit, split = blockIdx.z % p.nsplit;
     const double2* ag = p.a + (long long)g * p.a_sg;
     const double2* bg = p.b + (long long)g * p.b_sg;
     const int ktiles = (p.K + ZG_TK - 1) / ZG_TK;
-    const int total = ktiles * p.S;                    // pipeline steps: (segment, k-tile)
+    const int all_steps = ktiles * p.S;                // pipeline steps: (segment, k-tile)
+    const int first = (int)((long long)all_steps * split / p.nsplit);
+    const int total = (int)((long long)all_steps * (split + 1) / p.nsplit) - first;   // this CTA's share
 
     auto load_stage = [&](int step, int stage) {
         double2* sa = zsm + stage * ZG_STAGE_ELEMS;
         double2* sb = sa + ZG_A_ELEMS;
-        const int s = step / ktiles, k0 = (step % ktiles) * ZG_TK;
+        const int s = (first + step) / ktiles, k0 = ((first + step) % ktiles) * ZG_TK;
         const double2* as = ag + (long long)s * p.a_ss;
         const double2* bs = bg + (long long)s * p.b_ss;
         // A tile: 64 x 16 complex = 1024 elements, 4 per thread
@@ -124,20 +129,28 @@ __global__ void __launch_bounds__(ZG_THREADS, 2) zgemm_dmma_kernel(const ZgemmAr
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) bf[j] = sb[(kk + fk) * ZG_B_LD + wn * 16 + j * 8 + frow];
+            // four sweeps over the 8 tiles: consecutive DMMAs never touch the same accumulator
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    dmma(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
-                    dmma(cr[i][j][0], cr[i][j][1], af[i].y, -bf[j].y);
-                    dmma(ci[i][j][0], ci[i][j][1], af[i].x, bf[j].y);
-                    dmma(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
-                }
+                for (int j = 0; j < 2; ++j) dmma(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(ci[i][j][0], ci[i][j][1], af[i].x, bf[j].y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(cr[i][j][0], cr[i][j][1], af[i].y, -bf[j].y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(ci[i][j][0], ci[i][j][1], af[i].y, bf[j].x);
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // epilogue: lane holds C(row = lane/4, cols 2*(lane%4) + {0,1}) of every 8x8 tile
-    double2* cg = p.c + (long long)g * p.c_sg;
+    double2* cg = p.c + (long long)g * p.c_sg + (long long)split * p.c_ssplit;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -158,16 +171,18 @@ extern "C" {
 
 int32_t qca_zgemm_batched(const void* a, const void* b, void* c, int32_t M, int32_t N, int32_t K, int32_t S, int32_t G,
                           int64_t a_sg, int64_t a_ss, int64_t a_sm, int64_t a_sk, int64_t b_sg, int64_t b_ss,
-                          int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, void* stream) {
+                          int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, int32_t nsplit, int64_t c_ssplit,
+                          void* stream) {
     QCA_REQUIRE(a && b && c, QCA_ERR_ARG, "NULL argument");
     QCA_REQUIRE(M >= 1 && N >= 1 && K >= 1 && S >= 1 && G >= 1 && G <= 65535, QCA_ERR_ARG, "bad GEMM shape");
     QCA_REQUIRE(a_sm == 1 || a_sk == 1, QCA_ERR_ARG, "A needs a unit stride in m or in k");
+    QCA_REQUIRE(nsplit >= 1 && (long long)G * nsplit <= 65535, QCA_ERR_ARG, "bad split count %d", nsplit);
     qca::ZgemmArgs p{};
     p.a = (const double2*)a; p.b = (const double2*)b; p.c = (double2*)c;
     p.a_sg = a_sg; p.a_ss = a_ss; p.a_sm = a_sm; p.a_sk = a_sk;
     p.b_sg = b_sg; p.b_ss = b_ss; p.b_sk = b_sk; p.c_sg = c_sg; p.c_sm = c_sm;
-    p.M = M; p.N = N; p.K = K; p.S = S; p.G = G; p.conj_a = conj_a;
-    const dim3 grid((N + qca::ZG_TN - 1) / qca::ZG_TN, (M + qca::ZG_TM - 1) / qca::ZG_TM, G);
+    p.M = M; p.N = N; p.K = K; p.S = S; p.G = G; p.conj_a = conj_a; p.nsplit = nsplit; p.c_ssplit = c_ssplit;
+    const dim3 grid((N + qca::ZG_TN - 1) / qca::ZG_TN, (M + qca::ZG_TM - 1) / qca::ZG_TM, G * nsplit);
     // k contiguous in global memory: stage A as [m][k]; otherwise (m contiguous) as [k][m]
     auto kern = (a_sk == 1 && a_sm != 1) ? qca::zgemm_dmma_kernel<true> : qca::zgemm_dmma_kernel<false>;
     QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, qca::ZG_SMEM_BYTES));

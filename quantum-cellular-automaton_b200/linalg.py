@@ -80,36 +80,52 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     return u[:, order], s[order], v[:, order].conj().T, rest_norm
 
 
-def zgemm_batched(a, b, c, M, N, K, S, G, a_strides, b_strides, c_strides, conj_a=False):
-    """C_g[m,n] = sum_s sum_k A_{g,s}[m,k] B_{g,s}[k,n] on the FP64 tensor cores (csrc/qca_zgemm.cu).
-    a, b, c: complex128 CUDA tensors (only their storage is used); a_strides = (sg, ss, sm, sk),
-    b_strides = (sg, ss, sk), c_strides = (sg, sm), in elements."""
+_SM_COUNT = {}
+
+
+def _sm_count(device) -> int:
     import torch
-    stream = torch.cuda.current_stream(c.device).cuda_stream
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def zgemm_batched(a, b, out_shape, M, N, K, S, G, a_strides, b_strides, conj_a=False):
+    """C_g[m,n] = sum_s sum_k A_{g,s}[m,k] B_{g,s}[k,n] on the FP64 tensor cores (csrc/qca_zgemm.cu).
+    a, b: complex128 CUDA tensors (only their storage is used); a_strides = (sg, ss, sm, sk),
+    b_strides = (sg, ss, sk) in elements.  Returns C as a contiguous tensor of `out_shape`
+    (G * M * N elements).  When the tile grid would leave most SMs idle the reduction is split over
+    several CTAs per tile and the partial sums are added in a fixed order."""
+    import torch
+    tiles = -(-M // 64) * -(-N // 64) * G
+    steps = S * -(-K // 16)
+    nsplit = 1
+    target = 2 * _sm_count(a.device)
+    if tiles < target:
+        nsplit = max(1, min(target // tiles, steps // 4, 16))
+    out = torch.empty((nsplit,) + tuple(out_shape), dtype=a.dtype, device=a.device)
+    stream = torch.cuda.current_stream(a.device).cuda_stream
     _lib.check(_lib.lib.qca_zgemm_batched(
-        C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr()), M, N, K, S, G,
-        *[int(x) for x in a_strides], *[int(x) for x in b_strides], *[int(x) for x in c_strides],
-        int(conj_a), C.c_void_p(stream)))
-    return c
+        C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), M, N, K, S, G,
+        *[int(x) for x in a_strides], *[int(x) for x in b_strides], M * N, N,
+        int(conj_a), nsplit, G * M * N, C.c_void_p(stream)))
+    return out[0] if nsplit == 1 else out.sum(dim=0)
 
 
 def env_times_tensor(left, theta):
     """T[g, w, y, u] = sum_x left[x, w, y] * theta[g, x, u]   (first step of H_eff: L . theta)."""
-    import torch
     dx, w, dy = left.shape
     g, _, du = theta.shape
     left, theta = left.contiguous(), theta.contiguous()
-    out = torch.empty((g, w, dy, du), dtype=theta.dtype, device=theta.device)
-    return zgemm_batched(left, theta, out, M=w * dy, N=du, K=dx, S=1, G=g,
-                         a_strides=(0, 0, 1, w * dy), b_strides=(dx * du, 0, du), c_strides=(w * dy * du, du))
+    return zgemm_batched(left, theta, (g, w, dy, du), M=w * dy, N=du, K=dx, S=1, G=g,
+                         a_strides=(0, 0, 1, w * dy), b_strides=(dx * du, 0, du))
 
 
 def tensor_times_env(t, right):
     """out[g, y, v] = sum_{n,u} t[g, n, y, u] * right[u, n, v]   (last step of H_eff: T . R)."""
-    import torch
     g, w, dy, du = t.shape
     _, _, dv = right.shape
     t, right = t.contiguous(), right.contiguous()
-    out = torch.empty((g, dy, dv), dtype=t.dtype, device=t.device)
-    return zgemm_batched(t, right, out, M=dy, N=dv, K=du, S=w, G=g,
-                         a_strides=(w * dy * du, dy * du, du, 1), b_strides=(0, dv, w * dv), c_strides=(dy * dv, dv))
+    return zgemm_batched(t, right, (g, dy, dv), M=dy, N=dv, K=du, S=w, G=g,
+                         a_strides=(w * dy * du, dy * du, du, 1), b_strides=(0, dv, w * dv))
