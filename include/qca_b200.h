@@ -75,15 +75,24 @@ typedef struct qca_pass {
  * written to passes[0..capacity). */
 int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity, int32_t* npasses);
 
+/* Sharded register: global index-bit positions of the log2(world_size) sharded qubits, ascending
+ * (rank bit j <-> positions[j]).  Non-adjacent cells {0, d+1, 2(d+1)} when the register is large
+ * enough (every rank then pulls the same amount over NVLink), else the top qubits.  The local index
+ * of a rank is the global index with those bits removed. */
+int32_t qca_plan_shard(const qca_rule_t* rule, int32_t world_size, int32_t* positions);
+
 /* A rule term that flips a qubit held by another rank (sharded register): this rank adds
- * sign * [mask bit v set] * partner_vector[x] where v = top `distance` local bits of x. */
+ * sign * [mask bit v set] * partner_vector[x], same local index x on the partner. */
 typedef struct qca_remote_op {
     int32_t pass;    /* tile pass whose epilogue carries the term */
     int32_t partner; /* rank whose vector is read over NVLink */
     int32_t qubit;   /* index bit of the flipped qubit (>= local_bits) */
     int32_t sign;    /* +1 if this rank holds the qubit dead, -1 if alive */
-    uint32_t mask;   /* activity of the term per value of the top `distance` local bits */
-    int32_t shift;   /* local_bits - min(distance, local_bits) */
+    uint32_t mask;   /* activity of the term per value v = (local index >> shift) & 15 (the local bits
+                        within `distance` of the sharded qubit) */
+    int32_t shift;
+    int32_t window_bits; /* number of local bits the predicate reads (mask is valid when <= 4) */
+    int32_t reserved;
 } qca_remote_op_t;
 int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_op_t* ops,
                         int32_t capacity, int32_t* nops);

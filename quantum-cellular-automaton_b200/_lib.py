@@ -44,7 +44,7 @@ class PassStruct(C.Structure):
 
 class RemoteOpStruct(C.Structure):
     _fields_ = [("pass_", C.c_int32), ("partner", C.c_int32), ("qubit", C.c_int32), ("sign", C.c_int32),
-                ("mask", C.c_uint32), ("shift", C.c_int32)]
+                ("mask", C.c_uint32), ("shift", C.c_int32), ("window_bits", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ExactStats(C.Structure):
@@ -67,6 +67,7 @@ SYMBOLS = {
     "qca_spectral_bound": (C.c_int32, [C.POINTER(RuleStruct), _dp]),
     "qca_chebyshev_plan": (C.c_int32, [C.c_double, C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_passes": (C.c_int32, [C.c_int32, C.POINTER(PassStruct), C.c_int32, C.POINTER(C.c_int32)]),
+    "qca_plan_shard": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_remote": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.c_int32, C.POINTER(RemoteOpStruct), C.c_int32,
                                     C.POINTER(C.c_int32)]),
     "qca_exact_plane_flags": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -163,8 +164,17 @@ def plan_remote(rules, world_size: int, rank: int) -> list[dict]:
     check(lib.qca_plan_remote(C.byref(rs), world_size, rank, None, 0, C.byref(n)))
     buf = (RemoteOpStruct * max(n.value, 1))()
     check(lib.qca_plan_remote(C.byref(rs), world_size, rank, buf, max(n.value, 1), C.byref(n)))
-    return [dict(pass_index=o.pass_, partner=o.partner, qubit=o.qubit, sign=o.sign, mask=o.mask, shift=o.shift)
-            for o in buf[:n.value]]
+    return [dict(pass_index=o.pass_, partner=o.partner, qubit=o.qubit, sign=o.sign, mask=o.mask, shift=o.shift,
+                 window_bits=o.window_bits) for o in buf[:n.value]]
+
+
+def plan_shard(rules, world_size: int) -> list[int]:
+    """Global index-bit positions of the sharded qubits, ascending (rank bit j <-> positions[j])."""
+    nbits = world_size.bit_length() - 1
+    buf = (C.c_int32 * max(nbits, 1))()
+    rs = rule_struct(rules)
+    check(lib.qca_plan_shard(C.byref(rs), world_size, buf))
+    return [int(buf[j]) for j in range(nbits)]
 
 
 def measure_finish(sums: np.ndarray, ncells: int):

@@ -74,6 +74,30 @@ __host__ __device__ __forceinline__ I activity_word(I x, int distance, uint32_t 
     return act;
 }
 
+// How a rank-local amplitude index expands to the global basis-state index when the register is
+// sharded: the sharded qubits sit at global bit positions pos[0] < pos[1] < ... (rank bit j <-> pos[j]);
+// the local bits fill the remaining positions in order.
+struct ShardMap {
+    int nins;
+    int pos[3];
+    unsigned long long rank_or;  // this rank's values of the sharded qubits, already in place
+};
+
+__host__ __device__ __forceinline__ unsigned long long expand_index(unsigned long long x, const ShardMap& m) {
+    for (int i = 0; i < m.nins; ++i) {
+        const int p = m.pos[i];
+        x = ((x >> p) << (p + 1)) | (x & ((1ull << p) - 1ull));
+    }
+    return x | m.rank_or;
+}
+
+// global bit position of local bit g
+__host__ __device__ __forceinline__ int global_pos(int g, const ShardMap& m) {
+    for (int i = 0; i < m.nins; ++i)
+        if (g >= m.pos[i]) ++g;
+    return g;
+}
+
 __host__ __device__ __forceinline__ uint32_t interval_mask_of(int lo, int hi) {
     uint32_t m = 0;
     for (int c = (lo < 0 ? 0 : lo); c < hi && c < 32; ++c) m |= (1u << c);

@@ -38,7 +38,7 @@ __device__ __forceinline__ void atomic_max_abs(unsigned long long* slot, double 
 // staged: interleaved psi.  phi = i^{-popcount} psi, exact (swaps and negations only).
 __global__ void unpack_rotate_kernel(const double2* __restrict__ staged, double* __restrict__ re,
                                      double* __restrict__ im, unsigned long long offset,
-                                     unsigned long long count, unsigned long long prefix,
+                                     unsigned long long count, const ShardMap shard,
                                      unsigned long long* maxabs) {
     double mre = 0.0, mim = 0.0;
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -47,7 +47,7 @@ __global__ void unpack_rotate_kernel(const double2* __restrict__ staged, double*
         const unsigned long long x = offset + i;
         const double2 p = staged[i];
         double a, b;
-        switch (__popcll(x | prefix) & 3) {
+        switch (__popcll(expand_index(x, shard)) & 3) {
             case 0: a = p.x; b = p.y; break;
             case 1: a = p.y; b = -p.x; break;
             case 2: a = -p.x; b = -p.y; break;
@@ -69,14 +69,14 @@ __global__ void unpack_rotate_kernel(const double2* __restrict__ staged, double*
 // staged[i] = (gr + i gi) * i^{popcount + extra} * (re + i im)
 __global__ void pack_rotate_kernel(double2* __restrict__ staged, const double* __restrict__ re,
                                    const double* __restrict__ im, unsigned long long offset,
-                                   unsigned long long count, unsigned long long prefix, int extra_quarter) {
+                                   unsigned long long count, const ShardMap shard, int extra_quarter) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < count; i += stride) {
         const unsigned long long x = offset + i;
         const double a = re[x], b = im ? im[x] : 0.0;
         double2 p;
-        switch ((__popcll(x | prefix) + extra_quarter) & 3) {
+        switch ((__popcll(expand_index(x, shard)) + extra_quarter) & 3) {
             case 0: p.x = a; p.y = b; break;
             case 1: p.x = -b; p.y = a; break;
             case 2: p.x = -a; p.y = -b; break;
@@ -90,13 +90,13 @@ __global__ void pack_rotate_kernel(double2* __restrict__ staged, const double* _
 // amp[2*cell + s] = sqrt(1-p) (s=0) or sqrt(p) (s=1); cell 0 is the top bit.
 __global__ void product_state_kernel(double* __restrict__ re, double* __restrict__ im,
                                      const double* __restrict__ amp, int ncells, int local_bits,
-                                     unsigned long long prefix, unsigned long long* maxabs) {
+                                     const ShardMap shard, unsigned long long* maxabs) {
     double mre = 0.0, mim = 0.0;
     const unsigned long long n = 1ull << local_bits;
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const unsigned long long xf = i | prefix;
+        const unsigned long long xf = expand_index(i, shard);
         double v = 1.0;
         for (int cell = 0; cell < ncells; ++cell) {
             const int s = (int)((xf >> (ncells - 1 - cell)) & 1ull);
@@ -221,7 +221,8 @@ struct Engine {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    unsigned long long namps = 0, prefix = 0;
+    unsigned long long namps = 0;
+    ShardMap shard{};     // local index -> global basis-state index
     double* plane[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     int cur = 0;          // vector index of the resident state
     int nplanes = 0;      // 0: no state yet
@@ -230,6 +231,7 @@ struct Engine {
     double bound = 0.0;   // spectral bound R
     std::vector<qca_pass_t> passes;
     std::vector<qca_remote_op_t> remote;
+    double remote_fraction[64] = {};   // per sharded qubit (global bit): fraction of the plane its term reads
     double2* staging = nullptr;
     unsigned long long staging_amps = 0;
     unsigned long long* d_maxabs = nullptr;
@@ -240,6 +242,8 @@ struct Engine {
     int num_sms = 148;
     // window lookup tables of the fast pass kernel (device), one pair per pass
     std::vector<unsigned short*> d_tab_lo, d_tab_hi;
+    std::vector<int> win_shift;
+    std::vector<unsigned> win_mask;
     bool fast_path = false;
     // sharding
     unsigned long long* d_flags = nullptr;
@@ -292,11 +296,38 @@ static int32_t upload_table(Engine* e, const std::vector<unsigned short>& tab, u
 
 // The fast kernel needs full 13-bit tiles, window tables of sane size (distance <= 4) and, when
 // sharded, a later pass to carry the remote terms.
+// Table of a later pass: its flipped local bits [H0, H0+M) occupy the global positions G0..G1 (with
+// the sharded qubits that lie in between); the window is the global bits [G0-d, G1+d] and the entry
+// holds the predicates of the M LOCAL bits only (sharded positions squeezed out).
+static std::vector<unsigned short> span_table(Engine* e, const qca_pass_t& ps, int* win_shift, unsigned* win_mask) {
+    const int d = e->rule.distance;
+    const uint32_t imask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+    const int g0 = global_pos(ps.high_start, e->shard), g1 = global_pos(ps.high_start + ps.high_bits - 1, e->shard);
+    const int span = g1 - g0 + 1;
+    *win_shift = g0 - d;
+    *win_mask = (1u << (span + 2 * d)) - 1u;
+    std::vector<unsigned short> tab((size_t)1 << (span + 2 * d));
+    for (size_t w = 0; w < tab.size(); ++w) {
+        const unsigned long long act = activity_word<unsigned long long>((unsigned long long)w, d, imask) >> d;
+        unsigned out = 0;
+        for (int q = 0; q < ps.high_bits; ++q)
+            out |= (unsigned)((act >> (global_pos(ps.high_start + q, e->shard) - g0)) & 1ull) << q;
+        tab[w] = (unsigned short)out;
+    }
+    return tab;
+}
+
+// The fast kernel needs full 13-bit tiles, window tables of sane size (distance <= 4), every sharded
+// qubit above the first tile and, when sharded, a later pass to carry remote terms.
 static int32_t build_tables(Engine* e) {
     const int d = e->rule.distance;
     e->fast_path = (e->local_bits >= kTile) && d <= 4 && (e->world == 1 || e->passes.size() >= 2);
+    for (int j = 0; j < e->shard.nins; ++j) e->fast_path = e->fast_path && e->shard.pos[j] >= kTile;
+    for (const qca_remote_op_t& op : e->remote) e->fast_path = e->fast_path && op.mask != 0;
     e->d_tab_lo.assign(e->passes.size(), nullptr);
     e->d_tab_hi.assign(e->passes.size(), nullptr);
+    e->win_shift.assign(e->passes.size(), 0);
+    e->win_mask.assign(e->passes.size(), 0);
     if (!e->fast_path) return QCA_OK;
     const uint32_t imask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
     for (size_t i = 0; i < e->passes.size(); ++i) {
@@ -305,7 +336,9 @@ static int32_t build_tables(Engine* e) {
             QCA_CHECK(upload_table(e, window_table(9 - d, d, imask), &e->d_tab_lo[i]));
             QCA_CHECK(upload_table(e, window_table(4 + d, d, imask), &e->d_tab_hi[i]));
         } else {
-            QCA_CHECK(upload_table(e, window_table(ps.high_bits, d, imask), &e->d_tab_hi[i]));
+            int shift = 0; unsigned mask = 0;
+            QCA_CHECK(upload_table(e, span_table(e, ps, &shift, &mask), &e->d_tab_hi[i]));
+            e->win_shift[i] = shift; e->win_mask[i] = mask;
         }
     }
     return QCA_OK;
@@ -327,7 +360,9 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     const qca_pass_t& ps = e->passes[pass_index];
     a.low_bits = ps.low_bits; a.high_start = ps.high_start; a.high_bits = ps.high_bits;
     a.flip_mask = ps.flip_mask;
-    a.prefix = e->prefix;
+    a.shard = e->shard;
+    a.win_shift = e->win_shift[pass_index];
+    a.win_mask = e->win_mask[pass_index];
     a.distance = e->rule.distance;
     a.interval_mask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
     a.tab_lo = e->d_tab_lo[pass_index];
@@ -366,7 +401,7 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     double remote = 0.0;
     for (int k = 0; k < a.nstreams; ++k) {
         if (a.s[k].bit < 0) vecs += 1.0;
-        else remote += (double)__builtin_popcount(a.s[k].mask) / (double)(1u << std::min(e->rule.distance, e->local_bits));
+        else remote += e->remote_fraction[a.s[k].bit];
     }
     e->st.pass_bytes += vecs * (double)e->plane_bytes() * e->nplanes;
     e->st.remote_bytes += remote * (double)e->plane_bytes() * e->nplanes;
@@ -532,7 +567,7 @@ static int32_t upload_vector(Engine* e, int v, const double* host, bool track) {
         const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
         QCA_CUDA(cudaMemcpyAsync(e->staging, host + 2 * off, cnt * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
         unpack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
-            e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->prefix, e->d_maxabs + (track ? 0 : 2));
+            e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->shard, e->d_maxabs + (track ? 0 : 2));
         QCA_CUDA(cudaGetLastError());
         e->st.kernel_launches += 1;
     }
@@ -544,7 +579,7 @@ static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter
     for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
         const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
         pack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
-            e->staging, e->plane[v][0], both_planes ? e->plane[v][1] : nullptr, off, cnt, e->prefix, extra_quarter);
+            e->staging, e->plane[v][0], both_planes ? e->plane[v][1] : nullptr, off, cnt, e->shard, extra_quarter);
         QCA_CUDA(cudaGetLastError());
         e->st.kernel_launches += 1;
         QCA_CUDA(cudaMemcpyAsync(host + 2 * off, e->staging, cnt * sizeof(double2), cudaMemcpyDeviceToHost, e->stream));
@@ -565,7 +600,7 @@ static int32_t measure_partial(Engine* e, double* sums) {
         return (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + kMeasureThreads - 1) / kMeasureThreads, (unsigned long long)e->measure_blocks));
     };
     for (int bit = 0; bit < e->local_bits; ++bit) {
-        const int cell = n - 1 - bit;
+        const int cell = n - 1 - global_pos(bit, e->shard);
         const unsigned long long npairs = e->namps >> 1;
         const int blocks = blocks_for(npairs);
         measure_pairs_kernel<<<blocks, kMeasureThreads, 0, e->stream>>>(re, im, re, im, bit, npairs, e->d_partials);
@@ -577,7 +612,7 @@ static int32_t measure_partial(Engine* e, double* sums) {
     // sharded qubits: the rank holding the qubit dead pairs its slice with the partner's
     for (int j = 0; j < e->rank_bits; ++j) {
         if ((e->rank >> j) & 1) continue;
-        const int cell = n - 1 - (e->local_bits + j);
+        const int cell = n - 1 - e->shard.pos[j];
         const int partner = e->rank ^ (1 << j);
         const double* pre = e->peer_plane[partner][e->cur][0];
         const double* pim = e->nplanes == 2 ? e->peer_plane[partner][e->cur][1] : nullptr;
@@ -773,12 +808,15 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     e->rule = *rule; e->device = device; e->world = world_size; e->rank = rank; e->rank_bits = rank_bits;
     e->local_bits = rule->ncells - rank_bits;
     e->namps = 1ull << e->local_bits;
-    e->prefix = (unsigned long long)rank << e->local_bits;
+    qca::plan_shard(*rule, world_size, &e->shard, rank);
     e->flags = flags;
     e->num_sms = prop.multiProcessorCount;
     e->bound = qca::spectral_bound(*rule);
     qca::plan_passes(e->local_bits, e->passes);
     if (int32_t rc = qca::plan_remote(*rule, world_size, rank, e->remote)) { delete h; return rc; }
+    for (const qca_remote_op_t& op : e->remote)  // fraction of the plane the term reads on this rank
+        e->remote_fraction[op.qubit] = op.window_bits <= 4
+            ? (double)__builtin_popcount(op.mask & 0xffffu) / 16.0 : 1.0;   // the mask is replicated over 16 entries
     e->st.spectral_bound = e->bound;
     e->st.passes_per_apply = (int32_t)e->passes.size();
     e->st.local_bits = e->local_bits;
@@ -874,7 +912,7 @@ int32_t qca_exact_set_product_state(qca_exact_t h, const double* p_alive, int32_
     QCA_CHECK(qca::prepare_upload(e));
     QCA_CUDA(cudaMemcpyAsync(e->d_amp, amp.data(), amp.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     qca::product_state_kernel<<<qca::stream_blocks(e, e->namps), 256, 0, e->stream>>>(
-        e->plane[e->cur][0], e->plane[e->cur][1], e->d_amp, ncells, e->local_bits, e->prefix, e->d_maxabs);
+        e->plane[e->cur][0], e->plane[e->cur][1], e->d_amp, ncells, e->local_bits, e->shard, e->d_maxabs);
     QCA_CUDA(cudaGetLastError());
     e->st.kernel_launches += 1;
     QCA_CUDA(cudaStreamSynchronize(e->stream));  // amp is a host temporary

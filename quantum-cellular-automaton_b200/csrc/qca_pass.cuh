@@ -35,9 +35,9 @@ constexpr int kMaxFastStreams = 4;
 struct EpiStream {
     const double* ptr[2];  // per plane
     double coef;
-    unsigned mask;         // fast kernel: active iff (mask >> ((x >> shift) & 15)) & 1; ~0u = always
+    unsigned mask;         // fast kernel: active iff (mask >> ((x_local >> shift) & 15)) & 1; ~0u = always
     int shift;
-    int bit;               // generic kernel: active iff activity bit `bit` of x is set; -1 = always
+    int bit;               // generic kernel: active iff activity bit `bit` of the GLOBAL index is set; -1 = always
     int pad;
 };
 
@@ -48,14 +48,17 @@ struct PassArgs {
     EpiStream s[kMaxStreams];
     int nstreams;
     unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
-    unsigned long long prefix;     // rank << local_bits: the sharded qubits of this rank
+    ShardMap shard;                // local index -> global basis-state index (sharded qubits inserted)
+    int win_shift;                 // later passes: window of tab_hi = (global index >> win_shift) & win_mask
+    unsigned win_mask;
     unsigned long long ntiles;
     int low_bits, high_start, high_bits;  // tile = bits [0,low) U [high_start, high_start+high_bits)
     int distance;
     unsigned interval_mask;
     // window tables (fast kernel): entry[w] = activity of the middle K bits of the (K+2d)-bit window w
     const unsigned short* tab_lo;  // pass 0: K = 9-d, window = x bits [0,9) << d
-    const unsigned short* tab_hi;  // pass 0: K = 4+d, window = x bits [9-2d, 13+d); pass>=1: K = M, bits [H0-d, H0+M+d)
+    const unsigned short* tab_hi;  // pass 0: K = 4+d, window = global bits [9-2d, 13+d); pass>=1: the pass's
+                                   // flipped qubits' global span +-d (entries already compressed to local bits)
 };
 
 // ---------------------------------------------------------------------------
@@ -86,12 +89,11 @@ __global__ void __launch_bounds__(kPassThreads) pass_kernel_generic(const PassAr
         for (unsigned y = threadIdx.x; y < tile_elems; y += kPassThreads) {
             const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
             const unsigned long long act_all =
-                activity_word<unsigned long long>((unsigned long long)x | a.prefix, a.distance, a.interval_mask);
-            const I act = (I)act_all & (I)a.flip_mask;
+                activity_word<unsigned long long>(expand_index((unsigned long long)x, a.shard), a.distance, a.interval_mask);
             double acc = 0.0;
             for (int q = 0; q < T; ++q) {
-                const int g = q < L ? q : H0 + (q - L);
-                if ((act >> g) & 1) {
+                const int g = q < L ? q : H0 + (q - L);            // local bit of tile bit q
+                if (((a.flip_mask >> g) & 1ull) && ((act_all >> global_pos(g, a.shard)) & 1ull)) {
                     const double v = tile[y ^ (1u << q)];
                     acc += ((y >> q) & 1u) ? -v : v;  // K = sum_c P_c (sigma^-  -  sigma^+)_c
                 }
@@ -136,9 +138,19 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // Epilogue operands are streamed through per-thread rings of shared memory filled by cp.async from
 // kernel entry on: deep memory-level parallelism at no register cost.  kRingRowsTotal rows of
-// 4 KiB (256 threads x 16 B) are split evenly between the NOPS operand streams of the launch.
+// 4 KiB (256 threads x 16 B) are split between the operand streams of the launch: local operands
+// (HBM, ~1 us) get a short ring, remote ones (NVLink, several us) the rest.
 constexpr int kRingRowsTotal = 12;
 constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16;  // 112 KiB: 2 CTAs/SM
+
+// ring depth (rows of look-ahead) of an unconditional / a conditional stream
+__host__ __device__ constexpr int ring_unc(int nunc, int ncond) {
+    return ncond == 0 ? (nunc ? kRingRowsTotal / nunc : 1)
+         : (nunc == 0 ? 1 : (nunc == 1 ? (ncond == 1 ? 4 : (ncond == 2 ? 2 : 3)) : 3));
+}
+__host__ __device__ constexpr int ring_cond(int nunc, int ncond) {
+    return ncond == 0 ? 1 : (kRingRowsTotal - nunc * ring_unc(nunc, ncond)) / ncond;
+}
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
@@ -149,7 +161,10 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     constexpr int NOPS = NUNC + NCOND;
     constexpr int M = kTile - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
-    constexpr int RING = NOPS ? kRingRowsTotal / NOPS : 1;
+    constexpr int DU = ring_unc(NUNC, NCOND), DC = ring_cond(NUNC, NCOND);   // look-ahead per stream kind
+    constexpr int DMIN = NOPS == 0 ? 1 : (NUNC == 0 ? DC : (NCOND == 0 ? DU : (DU < DC ? DU : DC)));
+    constexpr int DMAX = NOPS == 0 ? 1 : (NUNC == 0 ? DC : (NCOND == 0 ? DU : (DU > DC ? DU : DC)));
+    static_assert(NUNC * DU + NCOND * DC <= kRingRowsTotal, "ring budget");
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
     static_assert(NOPS >= 0 && NOPS <= kMaxFastStreams, "streams");
     extern __shared__ double tile[];
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     const I x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
 
     double2* tile2 = reinterpret_cast<double2*>(tile);
-    double2* ring = tile2 + (1 << (kTile - 1));  // [NOPS][RING][256]
+    double2* ring = tile2 + (1 << (kTile - 1));  // stream k: [depth_k][256] rows, streams back to back
     auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
         const unsigned ye = (unsigned)e << kRowShift;
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
@@ -180,19 +195,28 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         if (k < NUNC) return true;
         return (a.s[k].mask >> ((unsigned)(x >> a.s[k].shift) & 15u)) & 1u;
     };
-    auto fetch_row = [&](int e) {  // issue the cp.async of every stream for row e into its ring slot
+    auto ring_slot = [&](int k, int e) -> double2* {   // k, e are compile-time after unrolling
+        const int depth = k < NUNC ? DU : DC;
+        const int base_row = k < NUNC ? k * DU : NUNC * DU + (k - NUNC) * DC;
+        return ring + ((base_row + (e % depth)) * kPassThreads + tid);
+    };
+    // iteration `it` (negative in the prologue) issues, for every stream, the row `it + depth_k`:
+    // remote streams run further ahead than local ones, one commit group per iteration
+    auto fetch_ahead = [&](int it) {
 #pragma unroll
         for (int k = 0; k < NOPS; ++k) {
-            const I x = row_x(e);
-            if (stream_on(k, x))
-                cp_async16(ring + ((k * RING + (e % RING)) * kPassThreads + tid), a.s[k].ptr[plane] + x);
+            const int e = it + (k < NUNC ? DU : DC);
+            if (e >= 0 && e < kRows && (it >= 0 || e < (k < NUNC ? DU : DC))) {
+                const I x = row_x(e);
+                if (stream_on(k, x)) cp_async16(ring_slot(k, e), a.s[k].ptr[plane] + x);
+            }
         }
     };
     // ---- start streaming the epilogue operands ------------------------------------------------
     if (NOPS) {
 #pragma unroll
-        for (int e = 0; e < RING; ++e) {
-            fetch_row(e);
+        for (int it = -DMAX; it < 0; ++it) {
+            fetch_ahead(it);
             cp_async_commit();
         }
     }
@@ -219,18 +243,20 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
 
     __syncthreads();
 
-    const I pfx = (I)a.prefix;
 #pragma unroll
     for (int e = 0; e < kRows; ++e) {
         unsigned la0, la1;
+        // windows are cut out of the GLOBAL index (sharded qubits of this rank inserted); every
+        // sharded position is >= 13, so local bits 0..12 are global bits 0..12
+        const unsigned long long xg = expand_index((unsigned long long)row_x(e), a.shard);
         if (FLIP_LOW) {
             const int S = 9 - d;
-            const unsigned w = (unsigned)((row_x(e) | pfx) >> (9 - 2 * d)) & ((1u << (4 + 3 * d)) - 1u);
+            const unsigned w = (unsigned)(xg >> (9 - 2 * d)) & ((1u << (4 + 3 * d)) - 1u);
             const unsigned hi_act = a.tab_hi[w];
             la0 = lo_act0 | (hi_act << S);
             la1 = lo_act1 | (hi_act << S);
         } else {
-            const unsigned w = (unsigned)((row_x(e) | pfx) >> (H0 - d)) & ((1u << (M + 2 * d)) - 1u);
+            const unsigned w = (unsigned)(xg >> a.win_shift) & a.win_mask;
             la0 = la1 = (unsigned)a.tab_hi[w] << L;
         }
         double acc0 = 0.0, acc1 = 0.0;
@@ -266,12 +292,12 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         r.x = a.gamma * acc0;
         r.y = a.gamma * acc1;
         if (NOPS) {
-            cp_async_wait<RING - 1>();  // the group of row e has landed (own data: no barrier needed)
+            cp_async_wait<DMIN - 1>();  // every stream's row e has landed (own data: no barrier needed)
             const I x = row_x(e);
 #pragma unroll
             for (int k = 0; k < NOPS; ++k) {
                 if (stream_on(k, x)) {
-                    const double2 sv = ring[(k * RING + (e % RING)) * kPassThreads + tid];
+                    const double2 sv = *ring_slot(k, e);
                     r.x = fma(a.s[k].coef, sv.x, r.x);
                     r.y = fma(a.s[k].coef, sv.y, r.y);
                 }
@@ -279,7 +305,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         }
         stg_stream(out + row_x(e), r);
         if (NOPS) {
-            if (e + RING < kRows) fetch_row(e + RING);  // refill the slot just consumed
+            fetch_ahead(e);  // refill the slots just consumed
             cp_async_commit();
         }
     }

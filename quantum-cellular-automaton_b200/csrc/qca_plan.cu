@@ -132,6 +132,28 @@ void plan_passes(int local_bits, std::vector<qca_pass_t>& out) {
     }
 }
 
+// Which qubits are sharded.  The partner-rank traffic of a sharded qubit's term is proportional to
+// how often its rule predicate holds on a rank, and for ADJACENT sharded cells that depends on the
+// rank itself (the rank whose top three cells are all alive pulls 2.75 planes per application, the
+// all-dead rank 0.25, and every barrier waits for the heaviest).  Cells spaced distance+1 apart do
+// not see each other, so every rank pulls the same amount (1.5 planes for distance 2, [2,4)); cell 0
+// (the chain end, cheapest predicate) is always one of them.  The scattered layout needs every
+// sharded position above the contiguous first tile (13 qubits) plus `distance` context bits and the
+// 16-entry remote mask (2*distance <= 4 window bits); otherwise the top qubits are sharded.
+void plan_shard(const qca_rule_t& r, int world, ShardMap* map, int rank) {
+    int rank_bits = 0;
+    while ((1 << rank_bits) < world) ++rank_bits;
+    const int N = r.ncells, n = N - rank_bits, d = r.distance;
+    map->nins = rank_bits;
+    const int lowest = N - 1 - (rank_bits - 1) * (d + 1);
+    const bool scattered = rank_bits >= 2 && d <= 2 && lowest >= kTileBits + d + 1;
+    for (int j = 0; j < rank_bits; ++j)
+        map->pos[j] = scattered ? N - 1 - (rank_bits - 1 - j) * (d + 1) : n + j;
+    map->rank_or = 0;
+    for (int j = 0; j < rank_bits; ++j)
+        if ((rank >> j) & 1) map->rank_or |= 1ull << map->pos[j];
+}
+
 int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_remote_op_t>& out) {
     out.clear();
     int rank_bits = 0;
@@ -140,21 +162,31 @@ int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_re
     QCA_REQUIRE(n >= 1, QCA_ERR_ARG, "ncells %d too small for %d ranks", r.ncells, world);
     std::vector<qca_pass_t> passes;
     plan_passes(n, passes);
-    const int dbits = std::min(r.distance, n);
+    ShardMap map{};
+    plan_shard(r, world, &map, rank);
     const uint32_t imask = interval_mask_of(r.act_lo, r.act_hi);
     for (int j = 0; j < rank_bits; ++j) {
         qca_remote_op_t op{};
-        op.qubit = n + j;
+        op.qubit = map.pos[j];
         op.partner = rank ^ (1 << j);
         op.sign = ((rank >> j) & 1) ? -1 : 1;
-        op.shift = n - dbits;
+        // the predicate of this qubit reads the local bits around the hole it leaves in the local index
+        const int hole = map.pos[j] - j;                    // local position of the first bit above it
+        const int below = std::min(r.distance, hole), above = std::min(r.distance, n - hole);
+        const int wbits = below + above;
+        op.shift = hole - below;
+        op.window_bits = wbits;
         bool any = false;
-        for (unsigned v = 0; v < (1u << dbits); ++v) {
-            const unsigned long long xf = ((unsigned long long)rank << n) | ((unsigned long long)v << op.shift);
-            const bool on = (activity_word<unsigned long long>(xf, r.distance, imask) >> op.qubit) & 1ull;
+        for (unsigned v = 0; v < (1u << wbits); ++v) {
+            const unsigned long long xg = expand_index((unsigned long long)v << op.shift, map);
+            const bool on = (activity_word<unsigned long long>(xg, r.distance, imask) >> op.qubit) & 1ull;
             any |= on;
-            if (on && v < 32) op.mask |= (1u << v);
+            if (on && v < 16) op.mask |= (1u << v);
         }
+        if (wbits > 4) op.mask = 0;   // too wide for the fast kernel's 16-entry mask: generic kernel only
+        else  // the kernel indexes with (x >> shift) & 15: bits above the window must not matter
+            for (unsigned v = (1u << wbits); v < 16; ++v)
+                if ((op.mask >> (v & ((1u << wbits) - 1u))) & 1u) op.mask |= (1u << v);
         if (!any) continue;  // this rank never sees the term (e.g. not enough alive cells above)
         out.push_back(op);
     }
@@ -221,6 +253,17 @@ int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity
         QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "pass buffer too small");
         memcpy(passes, v.data(), v.size() * sizeof(qca_pass_t));
     }
+    return QCA_OK;
+}
+
+int32_t qca_plan_shard(const qca_rule_t* rule, int32_t world_size, int32_t* positions) {
+    QCA_CHECK(qca::validate_rule(rule));
+    QCA_REQUIRE(world_size == 1 || world_size == 2 || world_size == 4 || world_size == 8, QCA_ERR_ARG,
+                "world_size must be 1, 2, 4 or 8 (got %d)", world_size);
+    QCA_REQUIRE(positions != nullptr, QCA_ERR_ARG, "positions is NULL");
+    qca::ShardMap map{};
+    qca::plan_shard(*rule, world_size, &map, 0);
+    for (int j = 0; j < map.nins; ++j) positions[j] = map.pos[j];
     return QCA_OK;
 }
 

@@ -1,5 +1,6 @@
-"""One process per GPU: the state vector is sharded over the top log2(P) qubits, rank r holding
-the contiguous slice ``psi[r*2^n:(r+1)*2^n]`` of ``MPS.as_vector()``.
+"""One process per GPU: the state vector is sharded over log2(P) qubits (``_lib.plan_shard``): cells
+{0, d+1, 2(d+1)} when the register is large enough -- every rank then pulls the same amount over
+NVLink -- else the top cells; rank r holds the amplitudes whose sharded qubits spell r.
 
 ``torch.distributed`` is plumbing only: it moves the 64-byte CUDA-IPC handles once at start-up,
 two booleans after a state upload and the 4*N measurement sums per measure.  The data path (terms
@@ -38,10 +39,29 @@ def gather_objects(obj, group=None) -> list:
     return out
 
 
-def local_slice(psi: np.ndarray, world: int, rank: int) -> np.ndarray:
-    """This rank's contiguous part of a full 2^N vector (top log2(world) bits == rank)."""
-    n = psi.shape[0] // world
-    return psi[rank * n:(rank + 1) * n]
+def local_indices(nbits_total: int, positions: list[int], rank: int) -> np.ndarray:
+    """Global basis-state index of every local amplitude of `rank`: the local index with the sharded
+    qubits (global bit positions `positions`, ascending, rank bit j <-> positions[j]) inserted."""
+    x = np.arange(1 << (nbits_total - len(positions)), dtype=np.int64)
+    for j, p in enumerate(positions):
+        x = ((x >> p) << (p + 1)) | (x & ((1 << p) - 1)) | (((rank >> j) & 1) << p)
+    return x
+
+
+def local_slice(psi: np.ndarray, positions: list[int], rank: int) -> np.ndarray:
+    """This rank's amplitudes of a full 2^N vector (a contiguous block when the top qubits are
+    sharded, a strided gather when the sharded cells are spread out)."""
+    nbits = int(psi.shape[0]).bit_length() - 1
+    return np.ascontiguousarray(psi[local_indices(nbits, positions, rank)])
+
+
+def assemble(slices: list[np.ndarray], positions: list[int]) -> np.ndarray:
+    """Inverse of local_slice over all ranks."""
+    nbits = int(sum(s.shape[0] for s in slices)).bit_length() - 1
+    full = np.empty(1 << nbits, dtype=slices[0].dtype)
+    for rank, part in enumerate(slices):
+        full[local_indices(nbits, positions, rank)] = part
+    return full
 
 
 def combine_measurements(partials: list[np.ndarray], ncells: int):
@@ -63,6 +83,7 @@ class ShardedExactEngine:
         self._eng = _lib.ExactEngine(rules, device=device, world_size=self.world, rank=self.rank, flags=flags,
                                      stream=stream)
         self.local_amps = self._eng.local_amps
+        self.positions = _lib.plan_shard(rules, self.world)
         if self.world > 1:
             table = np.stack(gather_objects(self._eng.ipc_handles(), group))
             self._eng.ipc_import(table)
@@ -84,7 +105,7 @@ class ShardedExactEngine:
         """psi: the full 2^N vector (each rank takes its slice) or this rank's slice."""
         arr = np.asarray(psi).reshape(-1)
         if arr.size == self.local_amps * self.world and self.world > 1:
-            arr = local_slice(arr, self.world, self.rank)
+            arr = local_slice(arr, self.positions, self.rank)
         self._eng.set_state(arr)
         self._resolve()
 
@@ -93,7 +114,7 @@ class ShardedExactEngine:
 
     def get_state(self) -> np.ndarray:
         """The full vector on every rank (host gather; for small registers and tests)."""
-        return np.concatenate(gather_objects(self._eng.get_state(), self.group))
+        return assemble(gather_objects(self._eng.get_state(), self.group), self.positions)
 
     # -- evolution -------------------------------------------------------------------------------
     def step(self, step_size: float, nsteps: int = 1) -> None:
@@ -107,8 +128,8 @@ class ShardedExactEngine:
     def apply_h(self, vec) -> np.ndarray:
         arr = np.asarray(vec).reshape(-1)
         if arr.size == self.local_amps * self.world and self.world > 1:
-            arr = local_slice(arr, self.world, self.rank)
-        return np.concatenate(gather_objects(self._eng.apply_h(arr), self.group))
+            arr = local_slice(arr, self.positions, self.rank)
+        return assemble(gather_objects(self._eng.apply_h(arr), self.group), self.positions)
 
     def norm2(self) -> float:
         return float(sum(gather_objects(self._eng.norm2(), self.group)))

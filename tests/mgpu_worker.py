@@ -33,7 +33,8 @@ def main() -> int:
     # (ncells, distance, lo, hi, state): generic kernel, 2-pass and 3-pass fast kernel regimes
     cases = [(10 + rbits, 1, 1, 2, "single"), (9 + rbits, 2, 2, 4, "equal_superposition"),
              (15 + rbits, 1, 1, 2, "blinker"), (17 + rbits, 2, 2, 4, "triple_blinker"),
-             (17 + rbits, 2, 1, 3, "gradient"), (23 + rbits, 2, 2, 4, "triple_blinker")]
+             (17 + rbits, 2, 1, 3, "gradient"), (19 + rbits, 1, 1, 2, "gradient"),   # scattered shard cells from here on
+             (23 + rbits, 2, 2, 4, "triple_blinker")]
     for (n, d, lo, hi, state) in cases:
         rules = qca_b200.Rules(n, range(lo, hi), d)
         plist = qca_b200.states.plist(state, rules)
@@ -56,7 +57,7 @@ def main() -> int:
             if ref is not None:
                 ref.step(1.0, 1)
         check(f"norm n={n} {state}", abs(eng.norm2() - 1.0) < 1e-11)
-        if n <= 21:
+        if n <= 22:
             full = eng.get_state()
             if ref is not None:
                 check(f"state n={n} {state}", np.abs(full - ref.get_state()).max() < 1e-11,
@@ -71,7 +72,7 @@ def main() -> int:
             if ref is not None:
                 check(f"apply_h n={n}", np.abs(hv - ref.apply_h(v)).max() < 1e-11)
         # general complex state: both planes, explicit upload of the full vector
-        if n <= 21:
+        if n <= 22:
             rng = np.random.default_rng(7 * n)
             psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
             psi /= np.linalg.norm(psi)

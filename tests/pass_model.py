@@ -28,9 +28,25 @@ def tile_indices(ps: dict, tile: int) -> np.ndarray:
     return base | (y & ((1 << L) - 1)) | ((y >> L) << H0)
 
 
+def expand(xs: np.ndarray, positions, rank: int) -> np.ndarray:
+    """local index -> global index: insert the sharded qubits (ascending global positions)."""
+    x = xs.copy()
+    for j, p in enumerate(positions):
+        x = ((x >> p) << (p + 1)) | (x & ((1 << p) - 1)) | (((rank >> j) & 1) << p)
+    return x
+
+
+def global_pos(g: int, positions) -> int:
+    for p in positions:
+        if g >= p:
+            g += 1
+    return g
+
+
 def apply_k_by_tiles(vec: np.ndarray, passes: list, nbits: int, ncells: int, distance: int, lo: int, hi: int,
-                     prefix: int = 0) -> np.ndarray:
-    """K vec, tile by tile exactly as the kernel stages it (real vector, one plane)."""
+                     positions=(), rank: int = 0) -> np.ndarray:
+    """K vec, tile by tile exactly as the kernel stages it (real vector, one plane).  `positions`,
+    `rank`: sharded register (the vector is this rank's local part)."""
     out = np.zeros_like(vec)
     for ps in passes:
         L, H0, M = ps["low_bits"], ps["high_start"], ps["high_bits"]
@@ -38,12 +54,14 @@ def apply_k_by_tiles(vec: np.ndarray, passes: list, nbits: int, ncells: int, dis
         for tile in range(1 << (nbits - T)):
             xs = tile_indices(ps, tile)
             stage = vec[xs]
-            act = activity(xs | prefix, ncells, distance, lo, hi) & ps["flip_mask"]
+            act = activity(expand(xs, positions, rank), ncells, distance, lo, hi)
             y = np.arange(1 << T)
             acc = np.zeros(1 << T)
             for q in range(T):
                 g = q if q < L else H0 + (q - L)
-                on = ((act >> g) & 1).astype(bool)
+                if not (ps["flip_mask"] >> g) & 1:
+                    continue
+                on = ((act >> global_pos(g, positions)) & 1).astype(bool)
                 partner = stage[y ^ (1 << q)]
                 sign = np.where((y >> q) & 1, -1.0, 1.0)
                 acc += np.where(on, sign * partner, 0.0)

@@ -26,51 +26,66 @@ def k_apply_full(vec, n, d, lo, hi):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("n,d,lo,hi", [(10, 1, 1, 2), (11, 2, 2, 4), (17, 2, 2, 4), (12, 3, 2, 5), (16, 1, 1, 3)])
+@pytest.mark.parametrize("n,d,lo,hi", [(10, 1, 1, 2), (11, 2, 2, 4), (17, 2, 2, 4), (12, 3, 2, 5), (16, 1, 1, 3),
+                                       (21, 1, 1, 2), (22, 2, 2, 4)])
 def test_remote_plan_reproduces_operator(world, n, d, lo, hi):
+    """Every rank applies its tile passes plus its remote terms (as planned by the C library, for the
+    sharded-qubit layout the C library chose: scattered cells for the larger registers, top cells
+    otherwise) and the ranks together reproduce the operator on the full register."""
+    if n >= 21 and world == 2:
+        pytest.skip("same layout as the smaller cases")
     rules = RuleNS(n, d, lo, hi)
     rbits = world.bit_length() - 1
     nl = n - rbits
+    positions = _lib.plan_shard(rules, world)
+    assert positions == sorted(positions) and len(positions) == rbits and positions[-1] == n - 1
+    scattered = rbits >= 2 and positions != list(range(nl, n))
+    assert scattered == (rbits >= 2 and d <= 2 and n - 1 - (rbits - 1) * (d + 1) >= 13 + d + 1)
     rng = np.random.default_rng(world * 100 + n)
     vec = rng.standard_normal(1 << n)
     want = k_apply_full(vec, n, d, lo, hi)
     passes = _lib.plan_passes(nl)
     got = np.zeros_like(vec)
     xl = np.arange(1 << nl, dtype=np.int64)
+    loads = []
     for rank in range(world):
-        mine = sharding.local_slice(vec, world, rank)
-        out = pass_model.apply_k_by_tiles(mine.copy(), passes, nl, n, d, lo, hi, prefix=rank << nl)
+        idx = sharding.local_indices(n, positions, rank)
+        assert np.array_equal(idx, pass_model.expand(xl, positions, rank))
+        mine = vec[idx]
+        out = pass_model.apply_k_by_tiles(mine.copy(), passes, nl, n, d, lo, hi, positions, rank)
         ops = _lib.plan_remote(rules, world, rank)
+        act = pass_model.activity(idx, n, d, lo, hi)
+        load = 0.0
         for op in ops:
-            assert op["partner"] == rank ^ (1 << (op["qubit"] - nl)) and 0 <= op["pass_index"] < len(passes)
-            assert op["sign"] == (-1 if (rank >> (op["qubit"] - nl)) & 1 else 1)
-            v = (xl >> op["shift"]) & 15
-            on = ((op["mask"] >> v) & 1).astype(bool) if d <= 4 else None
-            # the generic kernel's criterion: activity bit of the sharded qubit
-            act = pass_model.activity(xl | (rank << nl), n, d, lo, hi)
-            on_bit = ((act >> op["qubit"]) & 1).astype(bool)
-            if on is not None:
-                assert np.array_equal(on, on_bit)
-            partner = sharding.local_slice(vec, world, op["partner"])
+            j = positions.index(op["qubit"])
+            assert op["partner"] == rank ^ (1 << j) and 0 <= op["pass_index"] < len(passes)
+            assert op["sign"] == (-1 if (rank >> j) & 1 else 1)
+            on_bit = ((act >> op["qubit"]) & 1).astype(bool)      # the generic kernel's criterion
+            if op["window_bits"] <= 4:                            # the fast kernel's criterion
+                v = (xl >> op["shift"]) & 15
+                assert np.array_equal(((op["mask"] >> v) & 1).astype(bool), on_bit)
+            partner = vec[sharding.local_indices(n, positions, op["partner"])]
             out[on_bit] += op["sign"] * partner[on_bit]
+            load += on_bit.mean()
+        loads.append(load)
         if len(passes) > 1:  # spread over the passes: pass 0 takes at most one, later passes at most three
             per_pass = [sum(1 for op in ops if op["pass_index"] == p) for p in range(len(passes))]
             assert per_pass[0] <= 1 and max(per_pass) <= 3
-        # terms the plan dropped must really be inactive on this rank
         planned = {op["qubit"] for op in ops}
-        act = pass_model.activity(xl | (rank << nl), n, d, lo, hi)
-        for q in range(nl, n):
+        for q in positions:  # terms the plan dropped must really be inactive on this rank
             if q not in planned:
                 assert not ((act >> q) & 1).any()
-        got[rank << nl:(rank + 1) << nl] = out
+        got[idx] = out
     assert np.abs(got - want).max() < 1e-12
+    if scattered:  # the point of the scattered layout: every rank pulls the same amount over NVLink
+        assert max(loads) - min(loads) < 1e-12
 
 
-def measure_partial_model(psi_local, n, nl, rank, world, peers):
+def measure_partial_model(psi_local, n, nl, rank, world, peers, positions):
     """What qca_exact_measure_partial returns, restated in numpy (rotation drops out of |.|^2, |w|)."""
     sums = np.zeros(4 * n)
     for bit in range(nl):
-        cell = n - 1 - bit
+        cell = n - 1 - pass_model.global_pos(bit, positions)
         t = psi_local.reshape(-1, 2, 1 << bit)
         a0, a1 = t[:, 0, :], t[:, 1, :]
         w = np.vdot(a1, a0)  # sum a0 conj(a1)
@@ -78,7 +93,7 @@ def measure_partial_model(psi_local, n, nl, rank, world, peers):
     for j in range(world.bit_length() - 1):
         if (rank >> j) & 1:
             continue
-        cell = n - 1 - (nl + j)
+        cell = n - 1 - positions[j]
         other = peers[rank ^ (1 << j)]
         w = np.vdot(other, psi_local)
         sums[4 * cell:4 * cell + 4] = [np.vdot(psi_local, psi_local).real, np.vdot(other, other).real, w.real, w.imag]
@@ -95,10 +110,11 @@ def _gloo_worker(rank, world, port, n, ret):
         psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
         psi /= np.linalg.norm(psi)
         nl = n - (world.bit_length() - 1)
-        mine = sharding.local_slice(psi, world, rank)
+        positions = [3, 8][:world.bit_length() - 1] if world == 4 else [n - 1]   # scattered and top layouts
+        mine = sharding.local_slice(psi, positions, rank)
         slices = sharding.gather_objects(mine)
-        assert np.array_equal(np.concatenate(slices), psi)
-        part = measure_partial_model(mine, n, nl, rank, world, slices)
+        assert np.array_equal(sharding.assemble(slices, positions), psi)
+        part = measure_partial_model(mine, n, nl, rank, world, slices, positions)
         pop, dpop, ent, bonds = sharding.combine_measurements(sharding.gather_objects(part), n)
         pop_o, dpop_o, ent_o, bonds_o = oracle.measure_vector(psi, n)
         ok = (np.abs(pop - pop_o).max() < 1e-12 and np.abs(ent - ent_o).max() < 1e-11
