@@ -105,20 +105,38 @@ class TDVP(Algorithm):
 
     def measure(self, population, d_population, single_site_entropy, bond_dims) -> None:
         """MPS.measure (mps.py:100-140): sweep the orthogonality centre through the chain on the
-        device, one D2H copy of the N reduced density matrices at the end."""
+        device, one D2H copy of the N reduced density matrices at the end.
+
+        1tdvp mirrors the reference literally: the stored tensors are re-gauged in place with the
+        LAPACK-convention QR (its later numbers depend on that gauge).  2tdvp is gauge invariant, so
+        the sweep runs on a working copy with the library QR and the stored tensors -- and with them
+        the right environments -- stay valid: no re-canonicalisation after a measurement."""
         torch = _torch()
         n = len(self._A)
         assert n + 1 == len(bond_dims)
         bond_dims[:n] = [a.shape[1] for a in self._A]
         bond_dims[n] = self._A[-1].shape[2]
-        self._canonicalize(0)
-        self._gauge_dirty = True
         rhos = []
-        for site in range(n):
-            if site > 0:
-                self._shift_right(site - 1)
-            a = self._A[site].reshape(2, -1)
-            rhos.append(a @ a.conj().T)
+        if self.args.algorithm == "1tdvp" or self._gauge_dirty:
+            self._canonicalize(0)
+            self._gauge_dirty = True
+            for site in range(n):
+                if site > 0:
+                    self._shift_right(site - 1)
+                a = self._A[site].reshape(2, -1)
+                rhos.append(a @ a.conj().T)
+        else:
+            # right-canonical with centre 0 (state after a completed step): carry the centre matrix
+            carry = None
+            for site in range(n):
+                a = self._A[site]
+                if carry is not None:
+                    a = torch.einsum("xl,plr->pxr", carry, a)
+                flat = a.reshape(2, -1)
+                rhos.append(flat @ flat.conj().T)
+                if site < n - 1:
+                    s = a.shape
+                    _, carry = torch.linalg.qr(a.reshape(s[0] * s[1], s[2]), mode="r")
         rho = torch.stack(rhos).cpu().numpy()
         pop = rho[:, 1, 1].real
         population[...] = pop
