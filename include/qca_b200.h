@@ -199,6 +199,36 @@ int32_t qca_zgemm_batched(const void* a, const void* b, void* c, int32_t M, int3
                           void* stream);
 
 /* ------------------------------------------------------------------------
+ * Matrix-free effective Hamiltonian of TDVP and its Krylov exponential (csrc/qca_heff.cu).  Replaces
+ * TDVP._assemble_H_eff / _evolve_A (algorithms/tdvp.py:299-310, 350-365: a dense (g dl dr)^2 matrix per
+ * site) and lautils.timestep (lautils/lautils.py:58-82: eigh of it).  All pointers are DEVICE pointers,
+ * complex128 row-major in the reference's index order:
+ *   psi[g][x][u]   g = 1 (bond matrix), 2 (one site), 4 (two sites: (a, c) -> 2a + c); x < dl, u < dr
+ *   left[x][w][y]  (dl, wl, dl)        right[u][w][v]  (dr, wr, dr)
+ *   mix: CSR matrix with g*wr rows and g*wl columns, Mx[(g', n), (g, w)]: the site operator(s)
+ *        (one site: W[g, g', w, n]; two sites: sum_m W1[a,b,w,m] W2[c,d,m,n]; bond: identity)
+ *   H_eff psi [g'][y][v] = sum  Mx[(g',n),(g,w)] left[x][w][y] right[u][n][v] psi[g][x][u]
+ * Everything is enqueued on `stream`; nothing synchronises or allocates: the caller supplies
+ * `workspace` of qca_heff_workspace_bytes(h, krylov_dim) bytes (krylov_dim = 0 for qca_heff_apply).
+ * ---------------------------------------------------------------------- */
+typedef struct qca_heff {
+    const void* left;
+    const void* right;
+    const int32_t* mix_rowptr;   /* [g*wr + 1] */
+    const int32_t* mix_col;      /* [nnz] */
+    const void* mix_val;         /* [nnz] complex128 */
+    int32_t dl, dr, wl, wr, g;
+} qca_heff_t;
+int32_t qca_heff_workspace_bytes(const qca_heff_t* h, int32_t krylov_dim, uint64_t* bytes);
+/* out = H_eff psi */
+int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* workspace, uint64_t workspace_bytes,
+                       void* stream);
+/* out = exp(-i t H_eff) psi by krylov_dim (<= 64) Lanczos steps with full re-orthogonalisation; the small
+ * tridiagonal problem is solved on the device too (Jacobi).  out may alias psi. */
+int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t krylov_dim, double t, void* workspace,
+                      uint64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The state is sharded over the top
  * log2(world_size) qubits; terms that flip a sharded qubit read the partner
  * rank's vector directly over NVLink (CUDA IPC peer mapping).  The host side

@@ -57,6 +57,12 @@ class ExactStats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class HeffStruct(C.Structure):
+    _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("mix_rowptr", C.c_void_p), ("mix_col", C.c_void_p),
+                ("mix_val", C.c_void_p), ("dl", C.c_int32), ("dr", C.c_int32), ("wl", C.c_int32), ("wr", C.c_int32),
+                ("g", C.c_int32)]
+
+
 _dp = C.POINTER(C.c_double)
 
 # every symbol include/qca_b200.h declares: (restype, argtypes)
@@ -92,6 +98,10 @@ SYMBOLS = {
                                        C.c_void_p]),
     "qca_zgemm_batched": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 9
                           + [C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "qca_heff_workspace_bytes": (C.c_int32, [C.POINTER(HeffStruct), C.c_int32, C.POINTER(C.c_uint64)]),
+    "qca_heff_apply": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qca_heff_expm": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
+                                  C.c_uint64, C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

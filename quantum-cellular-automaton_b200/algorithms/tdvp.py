@@ -7,7 +7,9 @@ to bond dimension ~32.  Here the MPS, the MPO and the environments live on the d
 
 * H_eff is applied matrix-free:  out[b,y,v] = sum W[a,b,wl,wr] L[x,wl,y] R[u,wr,v] psi[a,x,u]
   in the L.psi -> W -> .R order (8 w chi^3 complex MACs for a two-site tensor instead of 16 chi^4),
-* exp(-i pi/2 delta H_eff) psi comes from a Lanczos recursion that never leaves the device (Krylov
+* exp(-i pi/2 delta H_eff) psi comes from a Lanczos recursion that never leaves the device
+  (csrc/qca_heff.cu: two DMMA GEMMs + a sparse site-operator mix per application, fused
+  re-orthogonalisation kernels, the small tridiagonal exponential by Jacobi on the device; Krylov
   dimension fixed from |delta| * spectral bound, no host synchronisation inside a sweep); tensors
   small enough for a dense solve (dimension <= DENSE_LIMIT) take the reference's exact route,
 * QR runs on the device with LAPACK's Householder conventions (csrc/qca_linalg.cu -- the
@@ -36,11 +38,10 @@ import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
-from ..linalg import env_times_tensor, gram_svd, householder_qr, tensor_times_env
+from ..linalg import SiteOperator, gram_svd, heff_expm, householder_qr
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
-DMMA_MIN_BOND = 16        # bonds from which the two heavy contractions run on the DMMA kernel
 KRYLOV_TOL = 1e-16
 
 
@@ -70,6 +71,8 @@ class TDVP(Algorithm):
         if args.algorithm not in ("1tdvp", "2tdvp"):
             raise NotImplementedError(f"algorithm {args.algorithm!r}: only 1tdvp and 2tdvp are implemented on the GPU")
         self._W = [torch.as_tensor(np.ascontiguousarray(w), dtype=self.ct, device=self.dev) for w in H.W]
+        self._W_host = [np.ascontiguousarray(w, dtype=np.complex128) for w in H.W]
+        self._ops: dict = {}      # site operators of the native H_eff, built on first use (H is constant)
         # ||H_eff|| <= ||H|| <= R: the Krylov dimension follows from |delta| * pi/2 * R
         self._bound = _lib.spectral_bound(args.rules)
         super().__init__(psi_0, H, args)
@@ -225,30 +228,16 @@ class TDVP(Algorithm):
         return torch.einsum("bmvl,bkv->lmk", t, a.conj())
 
     # -- effective Hamiltonians, matrix-free ------------------------------------------------------------
+    # (torch.einsum forms: only the dense route of tiny tensors uses them; everything else runs in
+    #  csrc/qca_heff.cu)
     def _apply_one_site(self, left, right, w, psi):
         torch = _torch()
-        self.heff_applications += 1
-        dl, dr, wl, wr = left.shape[0], right.shape[0], left.shape[1], right.shape[1]
-        self.heff_flops += 8.0 * (2 * wl * dl * dl * dr + 4 * wl * wr * dl * dr + 2 * wr * dl * dr * dr)
-        if min(dl, dr) >= DMMA_MIN_BOND:   # FP64 tensor-core path (csrc/qca_zgemm.cu)
-            t = env_times_tensor(left, psi)
-            t = torch.einsum("abwm,awyu->bmyu", w, t)
-            return tensor_times_env(t, right)
         t = torch.einsum("xwy,axu->awyu", left, psi)
         t = torch.einsum("abwm,awyu->bmyu", w, t)
         return torch.einsum("bmyu,umv->byv", t, right)
 
     def _apply_two_site(self, left, right, w1, w2, theta):
         torch = _torch()
-        self.heff_applications += 1
-        dl, dr, wl, wm, wr = left.shape[0], right.shape[0], left.shape[1], w1.shape[3], right.shape[1]
-        self.heff_flops += 8.0 * (4 * wl * dl * dl * dr + 8 * wl * wm * dl * dr + 8 * wm * wr * dl * dr
-                                  + 4 * wr * dl * dr * dr)
-        if min(dl, dr) >= DMMA_MIN_BOND:   # FP64 tensor-core path (csrc/qca_zgemm.cu)
-            t = env_times_tensor(left, theta.reshape(4, dl, dr)).reshape(2, 2, wl, dl, dr)
-            t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
-            t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)
-            return tensor_times_env(t.reshape(4, wr, dl, dr), right).reshape(2, 2, dl, dr)
         t = torch.einsum("xwy,acxu->acwyu", left, theta)
         t = torch.einsum("abwm,acwyu->bcmyu", w1, t)
         t = torch.einsum("cdmn,bcmyu->bdnyu", w2, t)
@@ -259,10 +248,26 @@ class TDVP(Algorithm):
         t = torch.einsum("xwy,xu->wyu", left, c)
         return torch.einsum("wyu,uwv->yv", t, right)
 
+    def _site_operator(self, kind, site):
+        """Device CSR of the site operator(s): ('one', i) -> W_i, ('two', i) -> W_i W_{i+1},
+        ('bond', w) -> identity on w MPO channels."""
+        key = (kind, site)
+        op = self._ops.get(key)
+        if op is None:
+            if kind == "one":
+                op = SiteOperator(self._W_host[site], device=self.dev)
+            elif kind == "two":
+                op = SiteOperator(self._W_host[site], self._W_host[site + 1], device=self.dev)
+            else:
+                op = SiteOperator(None, site, device=self.dev)
+            self._ops[key] = op
+        return op
+
     # -- exponentials (lautils.py:58-82) ------------------------------------------------------------------
-    def _expm_apply(self, apply, psi, delta):
-        """exp(-i pi/2 delta H_eff)^T psi in the reference's index convention: `apply` already is
-        the transposed action (psi contracted with the row index of the reference's H_eff)."""
+    def _expm_apply(self, apply, left, right, op, psi, delta):
+        """exp(-i pi/2 delta H_eff)^T psi in the reference's index convention: the contraction already
+        is the transposed action (psi contracted with the row index of the reference's H_eff).
+        `apply` is the einsum form of the same operator, used by the dense route only."""
         torch = _torch()
         dim = psi.numel()
         t = (math.pi / 2.0) * delta
@@ -274,31 +279,16 @@ class TDVP(Algorithm):
             phase = torch.exp(-1j * t * lam)
             return ((vec * phase) @ (vec.conj().T @ psi.reshape(-1))).reshape(psi.shape)
         m = min(krylov_dimension(abs(t) * self._bound), dim)
-        basis = torch.zeros((m,) + tuple(psi.shape), dtype=self.ct, device=self.dev)
-        alpha = torch.zeros(m, dtype=torch.float64, device=self.dev)
-        beta = torch.zeros(m, dtype=torch.float64, device=self.dev)
-        norm0 = torch.linalg.vector_norm(psi)
-        basis[0] = psi / norm0
-        flat = basis.reshape(m, -1)
-        for j in range(m):
-            wv = apply(basis[j]).reshape(-1)
-            alpha[j] = torch.vdot(flat[j], wv).real
-            # full re-orthogonalisation (twice is enough): m is small, this is two thin GEMVs
-            for _ in range(2):
-                wv = wv - flat[: j + 1].T @ (flat[: j + 1].conj() @ wv)
-            if j + 1 < m:
-                b = torch.linalg.vector_norm(wv)
-                ok = b > 1e-13
-                beta[j + 1] = torch.where(ok, b, torch.zeros_like(b))
-                flat[j + 1] = torch.where(ok, wv / torch.where(ok, b, torch.ones_like(b)), torch.zeros_like(wv))
-        tri = torch.diag(alpha) + torch.diag(beta[1:], 1) + torch.diag(beta[1:], -1)
-        lam, vec = torch.linalg.eigh(tri)
-        coef = (vec * torch.exp(-1j * t * lam)) @ vec[0, :].to(self.ct)  # exp(-i t T) e_0
-        return norm0 * torch.tensordot(coef.to(self.ct), basis, dims=1)
+        dl, dr = left.shape[0], right.shape[0]
+        self.heff_applications += m
+        # FP64 operations of the two tensor-core contractions L.psi and T.R (8 per complex MAC)
+        self.heff_flops += m * 8.0 * op.g * (op.wl * dl * dl * dr + op.wr * dl * dr * dr)
+        return heff_expm(left, right, op, psi, m, t).reshape(psi.shape)
 
     def _evolve_site(self, site, delta):
         left, right, w = self._env_left(site - 1), self._env_right(site + 1), self._W[site]
-        return self._expm_apply(lambda v: self._apply_one_site(left, right, w, v), self._A[site], delta)
+        return self._expm_apply(lambda v: self._apply_one_site(left, right, w, v), left, right,
+                                self._site_operator("one", site), self._A[site], delta)
 
     # -- two-site TDVP (tdvp.py:107-145, 271-296) ---------------------------------------------------------
     def _two_site(self, i, j):
@@ -307,17 +297,18 @@ class TDVP(Algorithm):
         left, right = self._env_left(i - 1), self._env_right(j + 1)
         w1, w2 = self._W[i], self._W[j]
         theta = torch.einsum("alm,bmr->ablr", al, ar)
-        new = self._expm_apply(lambda v: self._apply_two_site(left, right, w1, w2, v), theta, self.args.step_size / 2)
+        new = self._expm_apply(lambda v: self._apply_two_site(left, right, w1, w2, v), left, right,
+                               self._site_operator("two", i), theta, self.args.step_size / 2)
         dl, dr = al.shape[1], ar.shape[2]
         mat = new.permute(0, 2, 1, 3).reshape(2 * dl, 2 * dr)
         # singular values that truncation can never keep are not resolved one by one: with
         # stop_below = eps / (4 sqrt(n)) the unresolved rest has norm < eps, so the first index whose
         # tail norm is under eps (tdvp.py:290-292) always lies inside the resolved part
         eps = self.args.svd_epsilon
-        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))))
+        cap = min(self.args.max_bond_dim, 2 * min(dl, dr))
+        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))), need=cap, tail_floor=eps)
         tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
         below = (tail < eps).nonzero()
-        cap = min(self.args.max_bond_dim, 2 * min(dl, dr))
         keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
         ul = u.reshape(2, dl, -1)[:, :, :keep]
         vr = vh.reshape(-1, 2, dr).permute(1, 0, 2)[:, :keep, :]
@@ -347,7 +338,8 @@ class TDVP(Algorithm):
 
     # -- one-site TDVP (tdvp.py:65-105, 164-188) -----------------------------------------------------------
     def _evolve_bond(self, left, right, c):
-        return self._expm_apply(lambda v: self._apply_bond(left, right, v), c, -self.args.step_size / 2)
+        return self._expm_apply(lambda v: self._apply_bond(left, right, v), left, right,
+                                self._site_operator("bond", left.shape[1]), c, -self.args.step_size / 2)
 
     def _sweep_right_one_site(self):
         torch = _torch()

@@ -1,0 +1,470 @@
+// Matrix-free effective Hamiltonian of TDVP and its Krylov exponential, resident on the device.
+//
+// Replaces, for one site tensor / two-site tensor / bond matrix psi,
+//   TDVP._assemble_H_eff + _evolve_A   (algorithms/tdvp.py:299-310, 350-365: dense (g dl dr)^2 matrix)
+//   lautils.timestep / calculate_U      (lautils/lautils.py:45-82: eigh of that matrix)
+// by
+//   H_eff psi = (L . psi) -> site operator(s) -> (. R)                  [two DMMA GEMMs + a sparse mix]
+//   exp(-i t H_eff) psi = ||psi|| V exp(-i t T) e_0                     [m-step Lanczos, V and T on the device]
+// launched as one fixed sequence of kernels on the caller's stream: no host synchronisation, no
+// allocation (the caller passes a workspace).
+//
+// Index conventions are the reference's: psi[g][x][u], L[x][w][y], R[u][w][v]; g enumerates the physical
+// indices (1: bond matrix, 2: one site, 4: two sites, (a, c) -> 2a + c).  The site operators enter as
+// the sparse matrix  Mx[(g', n), (g, w)]  (two sites: sum_m W1[a,b,w,m] W2[c,d,m,n]) in CSR form:
+//   T1[g][w][y][u]  = sum_x L[x][w][y] psi[g][x][u]
+//   T3[g'][n][y][u] = sum_{g,w} Mx[(g',n),(g,w)] T1[g][w][y][u]
+//   out[g'][y][v]   = sum_{n,u} T3[g'][n][y][u] R[u][n][v]
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "qca_common.cuh"
+
+namespace qca {
+
+constexpr int HE_THREADS = 256;
+constexpr int HE_MAXK = 64;   // largest Krylov dimension
+
+// ---- deterministic block reductions -----------------------------------------------------------
+__device__ __forceinline__ double he_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void he_block_sum(double (&v)[NV], double* red /* [NV][8] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+        v[u] = he_warp_sum(v[u]);
+        if (lane == 0) red[u * 8 + warp] = v[u];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < HE_THREADS / 32; ++w) s += red[threadIdx.x * 8 + w];
+        red[threadIdx.x * 8] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NV; ++u) v[u] = red[u * 8];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void he_slice(long long dim, long long* s0, long long* s1) {
+    const long long chunk = (dim + gridDim.x - 1) / gridDim.x;
+    *s0 = (long long)blockIdx.x * chunk;
+    *s1 = (*s0 + chunk < dim) ? *s0 + chunk : dim;
+}
+
+// ---- site operator(s): sparse mix of the (g, w) channels, summing split-K partials on the way ---
+__global__ void __launch_bounds__(HE_THREADS)
+he_mix_kernel(const double2* __restrict__ t1, int nsplit, long long sstride, double2* __restrict__ t3,
+              const int* __restrict__ rowptr, const int* __restrict__ col, const double2* __restrict__ val,
+              int nrows, long long plane) {
+    for (long long s = (long long)blockIdx.x * HE_THREADS + threadIdx.x; s < plane; s += (long long)gridDim.x * HE_THREADS) {
+        for (int r = 0; r < nrows; ++r) {
+            double ar = 0.0, ai = 0.0;
+            for (int z = rowptr[r]; z < rowptr[r + 1]; ++z) {
+                const double2 c = val[z];
+                const double2* src = t1 + (long long)col[z] * plane + s;
+                double2 x = src[0];
+                for (int k = 1; k < nsplit; ++k) {
+                    const double2 y = src[(long long)k * sstride];
+                    x.x += y.x; x.y += y.y;
+                }
+                ar += c.x * x.x - c.y * x.y;
+                ai += c.x * x.y + c.y * x.x;
+            }
+            t3[(long long)r * plane + s] = make_double2(ar, ai);
+        }
+    }
+}
+
+// out = sum of split-K partials
+__global__ void __launch_bounds__(HE_THREADS)
+he_sum_kernel(double2* __restrict__ out, const double2* __restrict__ parts, int nsplit, long long sstride, long long dim) {
+    for (long long s = (long long)blockIdx.x * HE_THREADS + threadIdx.x; s < dim; s += (long long)gridDim.x * HE_THREADS) {
+        double2 x = parts[s];
+        for (int k = 1; k < nsplit; ++k) {
+            const double2 y = parts[(long long)k * sstride + s];
+            x.x += y.x; x.y += y.y;
+        }
+        out[s] = x;
+    }
+}
+
+// ---- Lanczos vector work --------------------------------------------------------------------------
+// partial[block][i] = sum over the block's slice of conj(V_i) w,  i < nvec.  parts != NULL: w is first
+// formed as the sum of the split-K partials of the second GEMM and stored.
+__global__ void __launch_bounds__(HE_THREADS)
+he_dots_kernel(double2* __restrict__ w, const double2* __restrict__ parts, int nsplit, long long sstride,
+               const double2* __restrict__ V, long long dim, int nvec, double2* __restrict__ partial) {
+    __shared__ double red[8 * 8];
+    long long s0, s1;
+    he_slice(dim, &s0, &s1);
+    if (parts) {
+        for (long long s = s0 + threadIdx.x; s < s1; s += HE_THREADS) {
+            double2 x = parts[s];
+            for (int k = 1; k < nsplit; ++k) {
+                const double2 y = parts[(long long)k * sstride + s];
+                x.x += y.x; x.y += y.y;
+            }
+            w[s] = x;   // re-read below by the same thread only
+        }
+    }
+    for (int i0 = 0; i0 < nvec; i0 += 4) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long long s = s0 + threadIdx.x; s < s1; s += HE_THREADS) {
+            const double2 x = w[s];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u < nvec) {
+                    const double2 v = V[(long long)(i0 + u) * dim + s];
+                    acc[2 * u] += v.x * x.x + v.y * x.y;       // conj(v) * x
+                    acc[2 * u + 1] += v.x * x.y - v.y * x.x;
+                }
+            }
+        }
+        he_block_sum<8>(acc, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u < nvec) partial[(long long)blockIdx.x * HE_MAXK + i0 + u] = make_double2(acc[2 * u], acc[2 * u + 1]);
+        }
+    }
+}
+
+// w -= sum_i c_i V_i with c_i = sum over blocks (fixed order) of partial[block][i].
+// alpha_out != NULL: alpha_out = Re c_{nvec-1} (Lanczos diagonal).  norm_partial != NULL: the block's
+// share of ||w||^2 after the update.
+__global__ void __launch_bounds__(HE_THREADS)
+he_update_kernel(double2* __restrict__ w, const double2* __restrict__ V, long long dim, int nvec,
+                 const double2* __restrict__ partial, int nparts, double* alpha_out, double* norm_partial) {
+    __shared__ double2 c[HE_MAXK];
+    __shared__ double red[8];
+    if (threadIdx.x < nvec) {
+        double cr = 0.0, ci = 0.0;
+        for (int b = 0; b < nparts; ++b) {
+            const double2 p = partial[(long long)b * HE_MAXK + threadIdx.x];
+            cr += p.x; ci += p.y;
+        }
+        c[threadIdx.x] = make_double2(cr, ci);
+        if (alpha_out && blockIdx.x == 0 && threadIdx.x == nvec - 1) *alpha_out = cr;
+    }
+    __syncthreads();
+    long long s0, s1;
+    he_slice(dim, &s0, &s1);
+    double nacc[1] = {0.0};
+    for (long long s = s0 + threadIdx.x; s < s1; s += HE_THREADS) {
+        double2 x = w[s];
+        for (int i = 0; i < nvec; ++i) {
+            const double2 v = V[(long long)i * dim + s];
+            const double2 ci = c[i];
+            x.x -= ci.x * v.x - ci.y * v.y;
+            x.y -= ci.x * v.y + ci.y * v.x;
+        }
+        w[s] = x;
+        nacc[0] += x.x * x.x + x.y * x.y;
+    }
+    if (norm_partial) {
+        he_block_sum<1>(nacc, red);
+        if (threadIdx.x == 0) norm_partial[blockIdx.x] = nacc[0];
+    }
+}
+
+// alpha = Re sum_blocks partial[block][0]   (last Lanczos step: only the diagonal entry is needed)
+__global__ void he_alpha_kernel(const double2* __restrict__ partial, int nparts, double* alpha_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double cr = 0.0;
+        for (int b = 0; b < nparts; ++b) cr += partial[(long long)b * HE_MAXK].x;
+        *alpha_out = cr;
+    }
+}
+
+__global__ void __launch_bounds__(HE_THREADS)
+he_norm_kernel(const double2* __restrict__ src, long long dim, double* __restrict__ norm_partial) {
+    __shared__ double red[8];
+    long long s0, s1;
+    he_slice(dim, &s0, &s1);
+    double nacc[1] = {0.0};
+    for (long long s = s0 + threadIdx.x; s < s1; s += HE_THREADS) {
+        const double2 x = src[s];
+        nacc[0] += x.x * x.x + x.y * x.y;
+    }
+    he_block_sum<1>(nacc, red);
+    if (threadIdx.x == 0) norm_partial[blockIdx.x] = nacc[0];
+}
+
+// dst = src / b with b = sqrt(sum of the norm partials, fixed order); a vanishing b (Krylov space
+// exhausted, tdvp never divides by it) gives dst = 0 and b_out = 0.
+__global__ void __launch_bounds__(HE_THREADS)
+he_normalize_kernel(double2* dst, const double2* src, long long dim,   // dst may alias src
+                    const double* __restrict__ norm_partial, int nparts, double* b_out) {
+    __shared__ double sh_inv;
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nparts; b += 32) s += norm_partial[b];
+        s = he_warp_sum(s);
+        if (threadIdx.x == 0) {
+            const double b = sqrt(s);
+            const bool ok = b > 1e-13;
+            sh_inv = ok ? 1.0 / b : 0.0;
+            if (blockIdx.x == 0) *b_out = ok ? b : 0.0;
+        }
+    }
+    __syncthreads();
+    const double inv = sh_inv;
+    long long s0, s1;
+    he_slice(dim, &s0, &s1);
+    for (long long s = s0 + threadIdx.x; s < s1; s += HE_THREADS) {
+        const double2 x = src[s];
+        dst[s] = make_double2(x.x * inv, x.y * inv);
+    }
+}
+
+// coef = norm0 * Z exp(-i t Lambda) Z^T e_0 for the m x m Lanczos matrix T = tridiag(beta, alpha, beta)
+// (lautils.py:45-55 applied to T).  One warp, cyclic Jacobi in shared memory: unconditionally accurate
+// for the small, possibly decoupled (beta = 0) matrices that occur here.
+__global__ void he_tridiag_expm_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int m,
+                                       const double* __restrict__ norm0, double t, double2* __restrict__ coef) {
+    extern __shared__ double jsm[];
+    double* A = jsm;            // m x m
+    double* Z = jsm + m * m;    // m x m, columns = eigenvectors
+    const int lane = threadIdx.x;
+    for (int e = lane; e < m * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        if (r == c) v = alpha[r];
+        else if (r == c + 1) v = beta[r];
+        else if (c == r + 1) v = beta[c];
+        A[e] = v;
+        Z[e] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int e = lane; e < m * m; e += 32) {
+            const int r = e / m, c = e % m;
+            if (r == c) diag += A[e] * A[e];
+            else off += A[e] * A[e];
+        }
+        off = he_warp_sum(off);
+        diag = he_warp_sum(diag);
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < m - 1; ++p) {
+            for (int q = p + 1; q < m; ++q) {
+                const double apq = A[p * m + q];
+                if (apq == 0.0) continue;       // uniform across the warp
+                const double app = A[p * m + p], aqq = A[q * m + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                __syncwarp();
+                for (int k = lane; k < m; k += 32) {
+                    if (k != p && k != q) {
+                        const double akp = A[k * m + p], akq = A[k * m + q];
+                        const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                        A[k * m + p] = np_; A[p * m + k] = np_;
+                        A[k * m + q] = nq_; A[q * m + k] = nq_;
+                    }
+                    const double zkp = Z[k * m + p], zkq = Z[k * m + q];
+                    Z[k * m + p] = c * zkp - s * zkq;
+                    Z[k * m + q] = s * zkp + c * zkq;
+                }
+                if (lane == 0) {
+                    A[p * m + p] = app - tt * apq;
+                    A[q * m + q] = aqq + tt * apq;
+                    A[p * m + q] = 0.0; A[q * m + p] = 0.0;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    const double n0 = *norm0;
+    for (int k = lane; k < m; k += 32) {
+        double cr = 0.0, ci = 0.0;
+        for (int l = 0; l < m; ++l) {
+            const double lam = A[l * m + l];
+            double sn, cs;
+            sincos(t * lam, &sn, &cs);
+            const double f = Z[k * m + l] * Z[l];   // Z[0][l]
+            cr += f * cs;
+            ci -= f * sn;
+        }
+        coef[k] = make_double2(n0 * cr, n0 * ci);
+    }
+}
+
+// out = sum_k coef_k V_k
+__global__ void __launch_bounds__(HE_THREADS)
+he_combine_kernel(double2* __restrict__ out, const double2* __restrict__ V, long long dim, int m,
+                  const double2* __restrict__ coef) {
+    __shared__ double2 c[HE_MAXK];
+    if (threadIdx.x < m) c[threadIdx.x] = coef[threadIdx.x];
+    __syncthreads();
+    for (long long s = (long long)blockIdx.x * HE_THREADS + threadIdx.x; s < dim; s += (long long)gridDim.x * HE_THREADS) {
+        double ar = 0.0, ai = 0.0;
+        for (int k = 0; k < m; ++k) {
+            const double2 v = V[(long long)k * dim + s];
+            ar += c[k].x * v.x - c[k].y * v.y;
+            ai += c[k].x * v.y + c[k].y * v.x;
+        }
+        out[s] = make_double2(ar, ai);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+struct HeffPlan {
+    long long plane, dim, t1, t3;
+    int ns1, ns2, nblocks, sms;
+    // workspace offsets in complex128 units
+    long long off_t1, off_t3, off_p2, off_v, off_partial, off_small, total;
+};
+
+static int he_sm_count() {
+    static int sms[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
+static int he_split(long long M, long long N, int G, long long steps, int sms) {
+    const long long tiles = ((M + 63) / 64) * ((N + 63) / 64) * G;
+    const long long target = 2ll * sms;
+    if (tiles >= target) return 1;
+    long long n = std::min<long long>(std::min<long long>(target / tiles, steps / 4), 16);
+    return (int)std::max<long long>(1, n);
+}
+
+static int32_t he_plan(const qca_heff_t* h, int m, HeffPlan* p) {
+    QCA_REQUIRE(h && h->left && h->right && h->mix_rowptr && h->mix_col && h->mix_val, QCA_ERR_ARG, "NULL argument");
+    QCA_REQUIRE(h->dl >= 1 && h->dr >= 1 && h->wl >= 1 && h->wr >= 1, QCA_ERR_ARG, "bad H_eff shape");
+    QCA_REQUIRE(h->g == 1 || h->g == 2 || h->g == 4, QCA_ERR_ARG, "g must be 1 (bond), 2 (one site) or 4 (two sites)");
+    QCA_REQUIRE(m >= 0 && m <= HE_MAXK, QCA_ERR_ARG, "Krylov dimension %d out of range (<= %d)", m, HE_MAXK);
+    p->sms = he_sm_count();
+    p->plane = (long long)h->dl * h->dr;
+    p->dim = p->plane * h->g;
+    p->t1 = p->plane * h->g * h->wl;
+    p->t3 = p->plane * h->g * h->wr;
+    p->ns1 = he_split((long long)h->wl * h->dl, h->dr, h->g, (h->dl + 15) / 16, p->sms);
+    p->ns2 = he_split(h->dl, h->dr, h->g, (long long)h->wr * ((h->dr + 15) / 16), p->sms);
+    p->nblocks = (int)std::max<long long>(1, std::min<long long>((p->dim + 2 * HE_THREADS - 1) / (2 * HE_THREADS), 2ll * p->sms));
+    long long o = 0;
+    p->off_t1 = o; o += p->t1 * p->ns1;
+    p->off_t3 = o; o += std::max(p->t3, p->dim);
+    p->off_p2 = o; o += p->dim * p->ns2;
+    p->off_v = o; o += p->dim * std::max(m, 1);
+    p->off_partial = o; o += (long long)p->nblocks * HE_MAXK;
+    p->off_small = o; o += 4 * HE_MAXK + p->nblocks;   // alpha, beta, norm0, coef, norm partials (doubles, padded)
+    p->total = o;
+    return QCA_OK;
+}
+
+// T1, T3 and the split-K partials of out = H_eff psi; the caller sums the ns2 partials at ws + off_p2
+static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* psi, double2* ws, cudaStream_t st) {
+    double2* t1 = ws + p.off_t1;
+    double2* t3 = ws + p.off_t3;
+    double2* p2 = ws + p.off_p2;
+    const int dl = h->dl, dr = h->dr, wl = h->wl, wr = h->wr, g = h->g;
+    // T1[g][w][y][u] = sum_x L[x][(w,y)] psi[g][x][u]
+    QCA_CHECK(qca_zgemm_batched(h->left, psi, t1, wl * dl, dr, dl, 1, g, 0, 0, 1, (int64_t)wl * dl, (int64_t)dl * dr, 0, dr,
+                                (int64_t)wl * dl * dr, dr, 0, p.ns1, p.t1, st));
+    const int mix_blocks = (int)std::max<long long>(1, std::min<long long>((p.plane + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
+    he_mix_kernel<<<mix_blocks, HE_THREADS, 0, st>>>(t1, p.ns1, p.t1, t3, h->mix_rowptr, h->mix_col, (const double2*)h->mix_val,
+                                                     g * wr, p.plane);
+    QCA_CUDA(cudaGetLastError());
+    // out[g][y][v] = sum_n sum_u T3[g][n][y][u] R[u][n][v]
+    QCA_CHECK(qca_zgemm_batched(t3, h->right, p2, dl, dr, dr, wr, g, (int64_t)wr * dl * dr, (int64_t)dl * dr, dr, 1, 0, dr,
+                                (int64_t)wr * dr, (int64_t)dl * dr, dr, 0, p.ns2, p.dim, st));
+    return QCA_OK;
+}
+
+}  // namespace qca
+
+extern "C" {
+
+int32_t qca_heff_workspace_bytes(const qca_heff_t* h, int32_t krylov_dim, uint64_t* bytes) {
+    QCA_REQUIRE(bytes, QCA_ERR_ARG, "NULL argument");
+    qca::HeffPlan p{};
+    QCA_CHECK(qca::he_plan(h, krylov_dim, &p));
+    *bytes = (uint64_t)p.total * sizeof(double2);
+    return QCA_OK;
+}
+
+int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* workspace, uint64_t workspace_bytes,
+                       void* stream) {
+    QCA_REQUIRE(psi && out && workspace, QCA_ERR_ARG, "NULL argument");
+    qca::HeffPlan p{};
+    QCA_CHECK(qca::he_plan(h, 0, &p));
+    QCA_REQUIRE(workspace_bytes >= (uint64_t)p.total * sizeof(double2), QCA_ERR_ARG, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* ws = (double2*)workspace;
+    QCA_CHECK(qca::he_apply(h, p, (const double2*)psi, ws, st));
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((p.dim + qca::HE_THREADS - 1) / qca::HE_THREADS, 8ll * p.sms));
+    qca::he_sum_kernel<<<blocks, qca::HE_THREADS, 0, st>>>((double2*)out, ws + p.off_p2, p.ns2, p.dim, p.dim);
+    QCA_CUDA(cudaGetLastError());
+    return QCA_OK;
+}
+
+int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t m, double t, void* workspace,
+                      uint64_t workspace_bytes, void* stream) {
+    using namespace qca;
+    QCA_REQUIRE(psi && out && workspace, QCA_ERR_ARG, "NULL argument");
+    QCA_REQUIRE(m >= 1, QCA_ERR_ARG, "Krylov dimension must be >= 1");
+    HeffPlan p{};
+    QCA_CHECK(he_plan(h, m, &p));
+    QCA_REQUIRE(workspace_bytes >= (uint64_t)p.total * sizeof(double2), QCA_ERR_ARG, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* ws = (double2*)workspace;
+    double2* V = ws + p.off_v;
+    double2* partial = ws + p.off_partial;
+    double* small = (double*)(ws + p.off_small);
+    double* alpha = small;                  // [HE_MAXK]
+    double* beta = small + HE_MAXK;         // [HE_MAXK], beta[j] couples j-1 and j
+    double* norm0 = small + 2 * HE_MAXK;    // [1] (+ padding)
+    double2* coef = (double2*)(small + 4 * HE_MAXK);            // [HE_MAXK] complex
+    double* normp = small + 6 * HE_MAXK;    // [nblocks]
+    const int nb = p.nblocks;
+    QCA_CUDA(cudaMemsetAsync(small, 0, 4 * HE_MAXK * sizeof(double), st));
+    he_norm_kernel<<<nb, HE_THREADS, 0, st>>>((const double2*)psi, p.dim, normp);
+    he_normalize_kernel<<<nb, HE_THREADS, 0, st>>>(V, (const double2*)psi, p.dim, normp, nb, norm0);
+    QCA_CUDA(cudaGetLastError());
+    for (int j = 0; j < m; ++j) {
+        QCA_CHECK(he_apply(h, p, V + (long long)j * p.dim, ws, st));
+        const double2* parts = ws + p.off_p2;
+        if (j + 1 < m) {
+            double2* w = V + (long long)(j + 1) * p.dim;
+            he_dots_kernel<<<nb, HE_THREADS, 0, st>>>(w, parts, p.ns2, p.dim, V, p.dim, j + 1, partial);
+            he_update_kernel<<<nb, HE_THREADS, 0, st>>>(w, V, p.dim, j + 1, partial, nb, alpha + j, nullptr);
+            // second Gram-Schmidt pass ("twice is enough"), then normalise
+            he_dots_kernel<<<nb, HE_THREADS, 0, st>>>(w, nullptr, 0, 0, V, p.dim, j + 1, partial);
+            he_update_kernel<<<nb, HE_THREADS, 0, st>>>(w, V, p.dim, j + 1, partial, nb, nullptr, normp);
+            he_normalize_kernel<<<nb, HE_THREADS, 0, st>>>(w, w, p.dim, normp, nb, beta + j + 1);
+        } else {
+            double2* w = ws + p.off_t3;   // scratch: T3 is dead after the second GEMM
+            he_dots_kernel<<<nb, HE_THREADS, 0, st>>>(w, parts, p.ns2, p.dim, V + (long long)j * p.dim, p.dim, 1, partial);
+            he_alpha_kernel<<<1, 32, 0, st>>>(partial, nb, alpha + j);
+        }
+        QCA_CUDA(cudaGetLastError());
+    }
+    const int jsm = 2 * m * m * (int)sizeof(double);
+    if (jsm > 48 * 1024)
+        QCA_CUDA(cudaFuncSetAttribute(he_tridiag_expm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jsm));
+    he_tridiag_expm_kernel<<<1, 32, jsm, st>>>(alpha, beta, m, norm0, t, coef);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((p.dim + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
+    he_combine_kernel<<<blocks, HE_THREADS, 0, st>>>((double2*)out, V, p.dim, m, coef);
+    QCA_CUDA(cudaGetLastError());
+    return QCA_OK;
+}
+
+}  // extern "C"

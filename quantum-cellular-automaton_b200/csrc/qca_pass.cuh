@@ -25,8 +25,9 @@ constexpr int kRegHigh = 4;    // local bits 9..12 are register rows
 constexpr int kRows = 1 << kRegHigh;
 constexpr int kRowShift = kTile - kRegHigh;  // 9
 
-constexpr int kMaxStreams = 6;       // generic kernel; the fast kernel takes at most kMaxFastStreams
-constexpr int kMaxFastStreams = 4;
+constexpr int kMaxStreams = 6;       // generic kernel; the fast kernel takes at most two local operands
+constexpr int kMaxRemoteSlots = 2;   // fast kernel: remote (partner-rank) operand slots per launch
+constexpr int kMaxRotations = 4;     // == largest number of tile passes the rotation spreads terms over
 
 // One epilogue operand:  out[x] += coef * [active(x)] * ptr[x].
 // Local recurrence operands (a, c) are unconditional; a *remote* operand is the partner rank's
@@ -41,12 +42,30 @@ struct EpiStream {
     int pad;
 };
 
+// Fast kernel, sharded register.  A remote slot carries, for every amplitude x, at most one of the
+// terms that flip a sharded qubit: which one depends on the rotation r(x) (a function of four local
+// index bits above the first tile), so that over the passes of one operator application every term
+// is applied exactly once for every x while every launch pulls the same share of the NVLink traffic.
+struct RemoteAlt {
+    const double* ptr[2];  // partner rank's copy of `in`, per plane (peer mapped)
+    double coef;           // gamma * sign
+    unsigned mask;         // active iff (mask >> ((x_local >> shift) & 15)) & 1; 0 = no term
+    int shift;
+};
+struct RemoteSlot {
+    RemoteAlt alt[kMaxRotations];
+};
+
 struct PassArgs {
     const double* in[2];   // vector the operator is applied to (plane 0/1)
     double* out[2];
     double gamma;
     EpiStream s[kMaxStreams];
     int nstreams;
+    RemoteSlot rs[kMaxRemoteSlots];   // fast kernel only
+    int nrem;
+    unsigned rot_word;     // r(x) = (rot_word >> 2 * ((x_local >> rot_shift) & 15)) & 3
+    int rot_shift;
     unsigned long long flip_mask;  // qubits (local index bits) whose terms this pass applies
     ShardMap shard;                // local index -> global basis-state index (sharded qubits inserted)
     int win_shift;                 // later passes: window of tab_hi = (global index >> win_shift) & win_mask
@@ -136,37 +155,80 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Epilogue operands are streamed through per-thread rings of shared memory filled by cp.async from
-// kernel entry on: deep memory-level parallelism at no register cost.  kRingRowsTotal rows of
-// 4 KiB (256 threads x 16 B) are split between the operand streams of the launch: local operands
-// (HBM, ~1 us) get a short ring, remote ones (NVLink, several us) the rest.
-constexpr int kRingRowsTotal = 12;
-constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16;  // 112 KiB: 2 CTAs/SM
-
-// ring depth (rows of look-ahead) of an unconditional / a conditional stream
-__host__ __device__ constexpr int ring_unc(int nunc, int ncond) {
-    return ncond == 0 ? (nunc ? kRingRowsTotal / nunc : 1)
-         : (nunc == 0 ? 1 : (nunc == 1 ? (ncond == 1 ? 4 : (ncond == 2 ? 2 : 3)) : 3));
+// ---- mbarrier / bulk-copy (TMA) primitives for the remote operand ring ----------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__host__ __device__ constexpr int ring_cond(int nunc, int ncond) {
-    return ncond == 0 ? 1 : (kRingRowsTotal - nunc * ring_unc(nunc, ncond)) / ncond;
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s: a partner's memory never answered; fail instead of hanging
+            printf("qca_b200: remote operand ring timed out (block %u)\n", blockIdx.x);
+            __trap();
+        }
+    }
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Epilogue operands are streamed through rings of shared memory, kRingRowsTotal rows of 4 KiB
+// (256 threads x 16 B), filled from kernel entry on: deep memory-level parallelism at no register cost.
+//   * local operands (HBM, ~1 us): per-thread cp.async, one commit group per row;
+//   * remote operands (partner rank over NVLink, several us): bulk copies issued per warp -- the 32
+//     pairs of a warp's row are 512 contiguous bytes (128-byte pieces when the tile keeps fewer than 6
+//     low bits) -- each row completing on its own mbarrier.  The two mechanisms are independent: a
+//     slow NVLink row never holds back the HBM rows behind it (with cp.async groups, which retire in
+//     order, it did), and the remote ring runs a full DC rows ahead.
+constexpr int kRingRowsTotal = 12;
+constexpr int kPassWarps = kPassThreads / 32;
+constexpr int kPassMbarBytes = kPassWarps * 8 * 8;  // up to 8 mbarriers per warp (slots x rows)
+constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16 + kPassMbarBytes;  // 112.5 KiB: 2 CTAs/SM
+
+// ring depth (rows of look-ahead) of a local / a remote operand
+__host__ __device__ constexpr int ring_unc(int nunc, int nrem) {
+    return nunc == 0 ? 0 : (nrem == 0 ? kRingRowsTotal / nunc : (nunc == 1 ? 4 : (nrem == 1 ? 3 : 2)));
+}
+__host__ __device__ constexpr int ring_rem(int nunc, int nrem) {
+    return nrem == 0 ? 0 : (nunc == 2 ? (nrem == 1 ? 6 : 4) : (nrem == 1 ? 8 : 4));
 }
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
-// NUNC unconditional epilogue streams (recurrence operands) come first, then NCOND conditional
-// ones (remote terms of sharded qubits); NUNC + NCOND <= 4.
-template <typename I, int L, bool FLIP_LOW, int NUNC, int NCOND>
+// NUNC local epilogue operands (recurrence vectors), NREM remote slots (terms of sharded qubits).
+template <typename I, int L, bool FLIP_LOW, int NUNC, int NREM>
 __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs a) {
-    constexpr int NOPS = NUNC + NCOND;
     constexpr int M = kTile - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
-    constexpr int DU = ring_unc(NUNC, NCOND), DC = ring_cond(NUNC, NCOND);   // look-ahead per stream kind
-    constexpr int DMIN = NOPS == 0 ? 1 : (NUNC == 0 ? DC : (NCOND == 0 ? DU : (DU < DC ? DU : DC)));
-    constexpr int DMAX = NOPS == 0 ? 1 : (NUNC == 0 ? DC : (NCOND == 0 ? DU : (DU > DC ? DU : DC)));
-    static_assert(NUNC * DU + NCOND * DC <= kRingRowsTotal, "ring budget");
+    constexpr int DU = ring_unc(NUNC, NREM), DC = ring_rem(NUNC, NREM);   // look-ahead per operand kind
+    constexpr int CHUNK_LANES = (L >= 6) ? 32 : (1 << (L - 1));  // lanes whose pairs are contiguous in global memory
+    constexpr int ISSUERS = 32 / CHUNK_LANES;                    // bulk copies per warp and row
+    static_assert(NUNC * DU + NREM * DC <= kRingRowsTotal, "ring budget");
+    static_assert(NREM * DC <= 8, "mbarrier budget");
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
-    static_assert(NOPS >= 0 && NOPS <= kMaxFastStreams, "streams");
+    static_assert(NUNC >= 0 && NUNC <= 2 && NREM >= 0 && NREM <= kMaxRemoteSlots, "operands");
+    static_assert(L >= 4, "rows of at least 128 bytes");
     extern __shared__ double tile[];
     const int plane = blockIdx.y;
     const double* __restrict__ in = a.in[plane];
@@ -174,6 +236,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     const int H0 = a.high_start;
     const int d = a.distance;
     const unsigned tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
     constexpr unsigned low_mask = (1u << L) - 1u;
 
     // tile base and this thread's part of the index
@@ -186,37 +249,66 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     const I x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
 
     double2* tile2 = reinterpret_cast<double2*>(tile);
-    double2* ring = tile2 + (1 << (kTile - 1));  // stream k: [depth_k][256] rows, streams back to back
+    double2* ring = tile2 + (1 << (kTile - 1));            // local operand k: rows [k*DU, (k+1)*DU)
+    double2* rring = ring + NUNC * DU * kPassThreads;      // remote slot k: rows [k*DC, (k+1)*DC)
+    const unsigned mbar0 = smem_u32(ring + kRingRowsTotal * kPassThreads) + warp * 64u;   // this warp's mbarriers
     auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
         const unsigned ye = (unsigned)e << kRowShift;
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
     };
-    auto stream_on = [&](int k, I x) -> bool {
-        if (k < NUNC) return true;
-        return (a.s[k].mask >> ((unsigned)(x >> a.s[k].shift) & 15u)) & 1u;
+    auto local_slot = [&](int k, int e) -> double2* {   // k, e are compile-time after unrolling
+        return ring + ((k * DU + (e % DU)) * kPassThreads + tid);
     };
-    auto ring_slot = [&](int k, int e) -> double2* {   // k, e are compile-time after unrolling
-        const int depth = k < NUNC ? DU : DC;
-        const int base_row = k < NUNC ? k * DU : NUNC * DU + (k - NUNC) * DC;
-        return ring + ((base_row + (e % depth)) * kPassThreads + tid);
+    auto remote_slot = [&](int k, int e) -> double2* {
+        return rring + ((k * DC + (e % DC)) * kPassThreads + tid);
     };
-    // iteration `it` (negative in the prologue) issues, for every stream, the row `it + depth_k`:
-    // remote streams run further ahead than local ones, one commit group per iteration
-    auto fetch_ahead = [&](int it) {
+    auto remote_bar = [&](int k, int e) -> unsigned { return mbar0 + (unsigned)(k * DC + (e % DC)) * 8u; };
+    // the term slot k carries at x (rotation), and whether it is active there
+    auto remote_alt = [&](int k, I x, bool* on) -> const RemoteAlt* {
+        const unsigned rot = (a.rot_word >> (2u * ((unsigned)(x >> a.rot_shift) & 15u))) & 3u;
+        const RemoteAlt* al = &a.rs[k].alt[rot];
+        *on = (al->mask >> ((unsigned)(x >> al->shift) & 15u)) & 1u;
+        return al;
+    };
+    // row e of every remote slot: the first lane of each contiguous piece issues its bulk copy (or just
+    // arrives when the term is inactive there: activity is constant over a piece)
+    auto remote_issue = [&](int e) {
 #pragma unroll
-        for (int k = 0; k < NOPS; ++k) {
-            const int e = it + (k < NUNC ? DU : DC);
-            if (e >= 0 && e < kRows && (it >= 0 || e < (k < NUNC ? DU : DC))) {
-                const I x = row_x(e);
-                if (stream_on(k, x)) cp_async16(ring_slot(k, e), a.s[k].ptr[plane] + x);
+        for (int k = 0; k < NREM; ++k) {
+            const I x = row_x(e);
+            bool on;
+            const RemoteAlt* al = remote_alt(k, x, &on);
+            if ((lane & (CHUNK_LANES - 1)) == 0) {
+                const unsigned bar = remote_bar(k, e);
+                if (on) {
+                    mbar_arrive_expect_tx(bar, CHUNK_LANES * 16);
+                    bulk_g2s(smem_u32(remote_slot(k, e)), al->ptr[plane] + x, CHUNK_LANES * 16, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
             }
         }
     };
-    // ---- start streaming the epilogue operands ------------------------------------------------
-    if (NOPS) {
+    auto local_fetch = [&](int e) {
 #pragma unroll
-        for (int it = -DMAX; it < 0; ++it) {
-            fetch_ahead(it);
+        for (int k = 0; k < NUNC; ++k) cp_async16(local_slot(k, e), a.s[k].ptr[plane] + row_x(e));
+    };
+    // ---- start streaming the epilogue operands: the far ones first ---------------------------------
+    if (NREM) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NREM * DC; ++i) mbar_init(mbar0 + i * 8u, ISSUERS);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < DC; ++e) remote_issue(e);
+    }
+    if (NUNC) {
+#pragma unroll
+        for (int e = 0; e < DU; ++e) {
+            local_fetch(e);
             cp_async_commit();
         }
     }
@@ -291,30 +383,47 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         double2 r;
         r.x = a.gamma * acc0;
         r.y = a.gamma * acc1;
-        if (NOPS) {
-            cp_async_wait<DMIN - 1>();  // every stream's row e has landed (own data: no barrier needed)
+        if (NUNC) {
+            cp_async_wait<(NUNC ? DU : 1) - 1>();  // row e of every local operand has landed (own data: no barrier needed)
+#pragma unroll
+            for (int k = 0; k < NUNC; ++k) {
+                const double2 sv = *local_slot(k, e);
+                r.x = fma(a.s[k].coef, sv.x, r.x);
+                r.y = fma(a.s[k].coef, sv.y, r.y);
+            }
+        }
+        if (NREM) {
             const I x = row_x(e);
 #pragma unroll
-            for (int k = 0; k < NOPS; ++k) {
-                if (stream_on(k, x)) {
-                    const double2 sv = *ring_slot(k, e);
-                    r.x = fma(a.s[k].coef, sv.x, r.x);
-                    r.y = fma(a.s[k].coef, sv.y, r.y);
+            for (int k = 0; k < NREM; ++k) {
+                bool on;
+                const RemoteAlt* al = remote_alt(k, x, &on);
+                if (on) {
+                    mbar_wait(remote_bar(k, e), (unsigned)(e / DC) & 1u);
+                    const double2 sv = *remote_slot(k, e);
+                    r.x = fma(al->coef, sv.x, r.x);
+                    r.y = fma(al->coef, sv.y, r.y);
                 }
             }
         }
         stg_stream(out + row_x(e), r);
-        if (NOPS) {
-            fetch_ahead(e);  // refill the slots just consumed
+        if (NUNC) {
+            if (e + DU < kRows) local_fetch(e + DU);  // refill the slots just consumed
             cp_async_commit();
+        }
+        if (NREM) {
+            if (e + DC < kRows) {
+                __syncwarp();  // every lane has read row e of the remote ring: its slots may be overwritten
+                remote_issue(e + DC);
+            }
         }
     }
 }
 
 // kernel tables, one translation unit per index type (qca_pass_u32.cu / qca_pass_u64.cu)
 typedef void (*PassKernel)(const PassArgs);
-PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int ncond);
-PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int ncond);
+PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int nrem);
+PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int nrem);
 PassKernel generic_pass_kernel(bool wide);
 
 }  // namespace qca

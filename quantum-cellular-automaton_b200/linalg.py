@@ -25,7 +25,8 @@ def householder_qr(mat, complete: bool = False):
     return q.T, r.T
 
 
-def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels: int = 6):
+def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels: int = 6, need: int | None = None,
+             tail_floor: float = 0.0):
     """Thin SVD of a complex128 CUDA matrix from Hermitian eigendecompositions of Gram matrices.
 
     cuSOLVER's SVD of a 512 x 512 complex128 matrix takes 60-130 ms on a B200 and was 88 % of a
@@ -40,6 +41,9 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     stop_below: singular values below it are not resolved individually (2TDVP never keeps them:
     tdvp.py:290-292 truncates where the tail norm drops under svd_epsilon); they are returned only
     through `rest_norm`, the Frobenius norm of the unresolved part.
+    need / tail_floor: once `need` singular values are resolved and everything beyond them (resolved
+    or not) still has Frobenius norm >= tail_floor, the caller's truncation is decided -- it keeps
+    exactly `need` (the bond cap; tdvp.py:289-293) -- and the deeper levels are skipped.
 
     Returns (u, s, vh, rest_norm): s descending, u[:, i] = mat @ v_i / s_i, mat ~= u diag(s) vh
     up to rest_norm.
@@ -47,7 +51,7 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     import torch
     m, n = mat.shape
     if m < n:  # work on the side with the smaller Gram matrix
-        u, s, vh, rest = gram_svd(mat.conj().T, stop_below, level_ratio, max_levels)
+        u, s, vh, rest = gram_svd(mat.conj().T, stop_below, level_ratio, max_levels, need, tail_floor)
         return vh.conj().T, s, u.conj().T, rest
     basis = None          # right-singular subspace still to be resolved (n x k), None = everything
     us, ss, vs = [], [], []
@@ -75,6 +79,13 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
         if keep == sig.shape[0]:
             break
         basis = v_here[:, keep:]
+        resolved = sum(x.shape[0] for x in ss)
+        if need is not None and resolved >= need:
+            rest = torch.linalg.vector_norm(mat @ basis)
+            beyond = torch.cat(ss)[need:]
+            if float(torch.sqrt((beyond * beyond).sum() + rest * rest)) >= tail_floor:   # one more host sync
+                rest_norm = rest
+                break
     u, s, v = torch.cat(us, dim=1), torch.cat(ss), torch.cat(vs, dim=1)
     order = torch.argsort(s, descending=True, stable=True)    # levels are ordered; ties inside noise only
     return u[:, order], s[order], v[:, order].conj().T, rest_norm
@@ -129,3 +140,112 @@ def tensor_times_env(t, right):
     t, right = t.contiguous(), right.contiguous()
     return zgemm_batched(t, right, (g, dy, dv), M=dy, N=dv, K=du, S=w, G=g,
                          a_strides=(w * dy * du, dy * du, du, 1), b_strides=(0, dv, w * dv))
+
+
+# -- matrix-free H_eff and its Krylov exponential (csrc/qca_heff.cu) -------------------------------------
+def site_operator_csr(w1, w2=None):
+    """CSR form of the site operator(s) between the two environment contractions of H_eff, as NUMPY
+    arrays (rowptr int32, col int32, val complex128) plus (g, wl, wr).
+
+    one site  (tdvp.py:350-365):  Mx[(b, m), (a, w)]       = W[a, b, w, m]
+    two sites (tdvp.py:280-283):  Mx[(b, d, n), (a, c, w)] = sum_m W1[a, b, w, m] W2[c, d, m, n]
+    w1 is None: bond matrix (tdvp.py:312-327), identity on the w2 = (wl) channels given as an int."""
+    import numpy as np
+    if w1 is None:
+        wl = wr = int(w2)
+        dense = np.eye(wl, dtype=np.complex128)
+        g = 1
+    elif w2 is None:
+        w1 = np.asarray(w1)
+        wl, wr = w1.shape[2], w1.shape[3]
+        dense = np.transpose(w1, (1, 3, 0, 2)).reshape(2 * wr, 2 * wl)
+        g = 2
+    else:
+        w1, w2 = np.asarray(w1), np.asarray(w2)
+        wl, wr = w1.shape[2], w2.shape[3]
+        full = np.einsum("abwm,cdmn->bdnacw", w1, w2)
+        dense = full.reshape(4 * wr, 4 * wl)
+        g = 4
+    rowptr = np.zeros(dense.shape[0] + 1, dtype=np.int32)
+    cols, vals = [], []
+    for r in range(dense.shape[0]):
+        nz = np.nonzero(dense[r])[0]
+        cols.append(nz.astype(np.int32))
+        vals.append(dense[r, nz].astype(np.complex128))
+        rowptr[r + 1] = rowptr[r] + nz.size
+    col = np.concatenate(cols) if cols else np.zeros(0, np.int32)
+    val = np.concatenate(vals) if vals else np.zeros(0, np.complex128)
+    if col.size == 0:   # keep the device arrays non-empty
+        col, val = np.zeros(1, np.int32), np.zeros(1, np.complex128)
+    return rowptr, col, val, (g, wl, wr)
+
+
+class SiteOperator:
+    """Device copy of ``site_operator_csr`` (built once per site / bond: H is constant)."""
+
+    def __init__(self, w1, w2=None, device=None):
+        import torch
+        rowptr, col, val, (self.g, self.wl, self.wr) = site_operator_csr(w1, w2)
+        self.rowptr = torch.as_tensor(rowptr, device=device)
+        self.col = torch.as_tensor(col, device=device)
+        self.val = torch.as_tensor(val, device=device)
+
+
+class _Workspace:
+    """One growing device buffer per device: H_eff calls are stream-ordered, so it can be shared."""
+    _buf = {}
+
+    @classmethod
+    def get(cls, nbytes: int, device):
+        import torch
+        key = (device.type, device.index)
+        buf = cls._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+            cls._buf[key] = buf
+        return buf
+
+
+def _heff_struct(left, right, op: SiteOperator):
+    import torch
+    assert left.is_cuda and left.dtype == torch.complex128 and right.dtype == torch.complex128
+    dl, wl, dl2 = left.shape
+    dr, wr, dr2 = right.shape
+    assert dl == dl2 and dr == dr2 and wl == op.wl and wr == op.wr, (left.shape, right.shape, op.wl, op.wr)
+    left, right = left.contiguous(), right.contiguous()
+    h = _lib.HeffStruct(left.data_ptr(), right.data_ptr(), op.rowptr.data_ptr(), op.col.data_ptr(), op.val.data_ptr(),
+                        dl, dr, wl, wr, op.g)
+    return h, (left, right)   # keep the contiguous copies alive until the launches are enqueued
+
+
+def heff_apply(left, right, op: SiteOperator, psi):
+    """H_eff psi (psi: (g, dl, dr) or any shape with g*dl*dr elements); returns a tensor like psi."""
+    import torch
+    h, keep = _heff_struct(left, right, op)
+    psi_c = psi.contiguous()
+    assert psi_c.numel() == op.g * h.dl * h.dr
+    nbytes = C.c_uint64()
+    _lib.check(_lib.lib.qca_heff_workspace_bytes(C.byref(h), 0, C.byref(nbytes)))
+    ws = _Workspace.get(nbytes.value, psi.device)
+    out = torch.empty_like(psi_c)
+    stream = torch.cuda.current_stream(psi.device).cuda_stream
+    _lib.check(_lib.lib.qca_heff_apply(C.byref(h), C.c_void_p(psi_c.data_ptr()), C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream)))
+    return out
+
+
+def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float):
+    """exp(-i t H_eff) psi by `krylov_dim` Lanczos steps, all on the device, no host synchronisation."""
+    import torch
+    h, keep = _heff_struct(left, right, op)
+    psi_c = psi.contiguous()
+    assert psi_c.numel() == op.g * h.dl * h.dr
+    nbytes = C.c_uint64()
+    _lib.check(_lib.lib.qca_heff_workspace_bytes(C.byref(h), int(krylov_dim), C.byref(nbytes)))
+    ws = _Workspace.get(nbytes.value, psi.device)
+    out = torch.empty_like(psi_c)
+    stream = torch.cuda.current_stream(psi.device).cuda_stream
+    _lib.check(_lib.lib.qca_heff_expm(C.byref(h), C.c_void_p(psi_c.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      int(krylov_dim), float(t), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                      C.c_void_p(stream)))
+    return out

@@ -45,3 +45,20 @@ def test_gram_svd_stops_below_the_truncation_floor():
     assert r < 128 and s.min() < 1e-3      # stopped early, but resolved well below any 2TDVP cut-off
     assert abs(float(rest) - np.sqrt((sigma[r:] ** 2).sum())) < 1e-12
     assert np.abs(s - sigma[:r]).max() < 1e-13
+
+
+def test_gram_svd_skips_levels_once_the_bond_cap_decides_the_truncation():
+    """At the bond cap 2TDVP keeps exactly `need` singular values as long as everything beyond them
+    still weighs >= svd_epsilon (tdvp.py:289-293): the deeper levels need not be resolved."""
+    rng = np.random.default_rng(2)
+    sigma = np.exp(-np.arange(128) * 36.0 / 128)
+    a = matrix_with_spectrum(128, 128, sigma, rng)
+    need = 20                                        # sigma[20] ~ 4e-3: inside the first level
+    u, s, vh, rest = gram_svd(torch.as_tensor(a), stop_below=1e-16, need=need, tail_floor=1e-14)
+    s, r = s.numpy(), len(s)
+    assert need <= r < 64
+    assert np.abs(s[:need] - sigma[:need]).max() < 1e-13
+    assert abs(float(rest) - np.sqrt((sigma[r:] ** 2).sum())) < 1e-12
+    # when the tail beyond `need` is lighter than the floor the spectrum is resolved as before
+    u2, s2, vh2, rest2 = gram_svd(torch.as_tensor(a), stop_below=1e-16, need=need, tail_floor=1.0)
+    assert len(s2) == 128

@@ -185,3 +185,87 @@ def test_dmma_contractions_match_einsum(dx, w, du, g):
     got = tensor_times_env(t, right)
     want = torch.einsum("gnyu,unv->gyv", t, right)
     assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+
+
+def _mpo_pair(ncells=10, distance=1, lo=1, hi=2):
+    rules = qca_b200.Rules(ncells, range(lo, hi), distance)
+    w = qca_b200.MPO.hamiltonian_from_rules(rules).W
+    return np.asarray(w[ncells // 2 - 1]), np.asarray(w[ncells // 2])
+
+
+@pytest.mark.parametrize("dl,dr,distance", [(1, 3, 1), (3, 5, 1), (16, 16, 1), (40, 24, 2), (64, 64, 1), (96, 130, 1)])
+def test_native_heff_apply_matches_einsum(dl, dr, distance):
+    """csrc/qca_heff.cu (L.psi -> sparse site-operator mix -> .R) against the einsum form of the same
+    contraction (tdvp.py:299-310 / 350-365 without the dense matrix), for the two-site tensor, the
+    one-site tensor and the bond matrix."""
+    import torch
+    from qca_b200.linalg import SiteOperator, heff_apply
+    w1, w2 = _mpo_pair(distance=distance, lo=distance, hi=2 * distance)
+    wl, wm, wr = w1.shape[2], w1.shape[3], w2.shape[3]
+    gen = torch.Generator(device="cuda").manual_seed(dl * 1000 + dr)
+    def rnd(*shape):
+        return torch.randn(*shape, dtype=torch.complex128, device="cuda", generator=gen)
+    t1, t2 = torch.as_tensor(w1, device="cuda"), torch.as_tensor(w2, device="cuda")
+    # two sites
+    left, right, theta = rnd(dl, wl, dl), rnd(dr, wr, dr), rnd(2, 2, dl, dr)
+    got = heff_apply(left, right, SiteOperator(w1, w2, device="cuda"), theta)
+    t = torch.einsum("xwy,acxu->acwyu", left, theta)
+    t = torch.einsum("abwm,acwyu->bcmyu", t1, t)
+    t = torch.einsum("cdmn,bcmyu->bdnyu", t2, t)
+    want = torch.einsum("bdnyu,unv->bdyv", t, right)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+    # one site
+    right1, psi = rnd(dr, wm, dr), rnd(2, dl, dr)
+    got = heff_apply(left, right1, SiteOperator(w1, device="cuda"), psi)
+    t = torch.einsum("xwy,axu->awyu", left, psi)
+    t = torch.einsum("abwm,awyu->bmyu", t1, t)
+    want = torch.einsum("bmyu,umv->byv", t, right1)
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+    # bond
+    right0, c = rnd(dr, wl, dr), rnd(dl, dr)
+    got = heff_apply(left, right0, SiteOperator(None, wl, device="cuda"), c)
+    t = torch.einsum("xwy,xu->wyu", left, c)
+    want = torch.einsum("wyu,uwv->yv", t, right0)
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("chi,m,t", [(4, 24, 0.3), (8, 40, 1.1), (12, 12, 0.02), (8, 64, 2.0)])
+def test_native_krylov_exponential_matches_dense(chi, m, t):
+    """qca_heff_expm (Lanczos + Jacobi on the device) against exp(-i t H_eff) psi with H_eff assembled
+    densely as the reference does (lautils.py:45-55), on the environments of a real MPS."""
+    import torch
+    from qca_b200.linalg import heff_expm
+    n = 10
+    rules = qca_b200.Rules(n, range(1, 2), 1)
+    rng = np.random.default_rng(chi)
+    dims = [min(2 ** i, 2 ** (n - i), chi) for i in range(n + 1)]
+    mps = qca_b200.MPS([(rng.standard_normal((2, dims[i], dims[i + 1])) + 1j * rng.standard_normal((2, dims[i], dims[i + 1])))
+                        for i in range(n)])
+    args = qca_b200.Args(rules=rules, step_size=0.1, algorithm="2tdvp", max_bond_dim=chi, svd_epsilon=1e-14)
+    algo = qca_b200.TDVP(mps, qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    # left environments up to the middle of the chain
+    for site in range(n // 2 - 1):
+        algo._shift_right(site)
+        algo._left[site] = algo._grow_left(algo._env_left(site - 1), algo._A[site], algo._W[site])
+    i = n // 2 - 1
+    left, right = algo._env_left(i - 1), algo._env_right(i + 2)
+    theta = torch.einsum("alm,bmr->ablr", algo._A[i], algo._A[i + 1])
+    dim = theta.numel()
+    eye = torch.eye(dim, dtype=torch.complex128, device="cuda").reshape((dim,) + tuple(theta.shape))
+    h = torch.stack([algo._apply_two_site(left, right, algo._W[i], algo._W[i + 1], eye[k]).reshape(-1) for k in range(dim)], dim=1)
+    assert (h - h.conj().T).abs().max().item() < 1e-10 * h.abs().max().item()
+    lam, vec = torch.linalg.eigh(0.5 * (h + h.conj().T))
+    want = (vec * torch.exp(-1j * t * lam)) @ (vec.conj().T @ theta.reshape(-1))
+    got = heff_expm(left, right, algo._site_operator("two", i), theta, min(m, dim), t).reshape(-1)
+    assert (got - want).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item())
+    # one-site tensor, backwards in time (tdvp.py:120-127)
+    left1, right1 = algo._env_left(i - 1), algo._env_right(i + 1)
+    psi = algo._A[i]
+    dim = psi.numel()
+    eye = torch.eye(dim, dtype=torch.complex128, device="cuda").reshape((dim,) + tuple(psi.shape))
+    h = torch.stack([algo._apply_one_site(left1, right1, algo._W[i], eye[k]).reshape(-1) for k in range(dim)], dim=1)
+    lam, vec = torch.linalg.eigh(0.5 * (h + h.conj().T))
+    want = (vec * torch.exp(1j * t * lam)) @ (vec.conj().T @ psi.reshape(-1))
+    got = heff_expm(left1, right1, algo._site_operator("one", i), psi, min(m, dim), -t).reshape(-1)
+    assert (got - want).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item())
