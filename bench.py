@@ -246,11 +246,20 @@ def b200_arm(args) -> None:
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (None if absent)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "pass_kernel_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(f"N{args.num_cells}_g{world}")
+        if rec and planes == rec.get("planes"):
+            traffic = rec["dram_bytes_per_launch"]
+    applies = max(pst["pass_launches"] // max(pst["passes_per_apply"], 1), 1)
     bytes_per_launch = pst["pass_bytes"] / max(pst["pass_launches"], 1)
     avg_ms = pst["profiled_pass_ms"] / max(pst["profiled_pass_launches"], 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "qca::pass_kernel_v2 (tile pass of the rule operator + fused Clenshaw update)",
+                "traffic": traffic, "kernel": "qca::pass_kernel_v2 (tile pass of the rule operator + fused Clenshaw update)",
+                "avg_launch_ms_by_pass": [m / applies for m in pst["profiled_ms_by_pass"][:pst["passes_per_apply"]]],
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": pst["pass_launches"],
                 "peak_source": peak_src, "whole_step_gbs": whole_step_gbs, "per_gpu": True,
                 "nvlink_read_gbs_per_gpu": nvlink_gbs,
@@ -361,6 +370,13 @@ def tdvp_leg(args, device: int) -> dict:
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     flops, napply = algo.heff_flops, algo.heff_applications
+    # the contraction kernel itself, in situ: one more time step with an event pair around every
+    # launch of the DMMA kernel (all bond sizes of the chain, L2 state as in the real sweep)
+    from qca_b200 import _lib
+    _lib.zgemm_profile(True)
+    algo.do_time_step()
+    torch.cuda.synchronize()
+    zp = _lib.zgemm_profile(False)
     # through the plug-in API with a measurement every step (D2H of the N density matrices)
     t1 = time.perf_counter()
     for _ in range(args.tdvp_steps):
@@ -376,7 +392,8 @@ def tdvp_leg(args, device: int) -> dict:
     g0.record(); torch.matmul(a, b); torch.matmul(a, b); g1.record(); torch.cuda.synchronize()
     dgemm_tflops = 2 * 2.0 * 8192 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
     del a, b
-    achieved = flops / (ms * 1e-3) / 1e12
+    whole = flops / (ms * 1e-3) / 1e12
+    achieved = zp["flops"] / (zp["ms"] * 1e-3) / 1e12 if zp["ms"] > 0 else 0.0
     return {"metric": "2TDVP sweeps/s at chi=256", "value": 2 * args.tdvp_steps / (ms * 1e-3), "unit": "sweeps/s",
             "ms_per_time_step": ms / args.tdvp_steps, "steps": args.tdvp_steps, "init_s": init_s,
             "config": {"workload": f"2tdvp, --num-cells {n}, --max-bond-dim {chi}, distance 1, interval [1,2), step 0.005, "
@@ -384,9 +401,14 @@ def tdvp_leg(args, device: int) -> dict:
             "heff_applications_per_step": napply / args.tdvp_steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_tflops, "unit": "TFLOP/s",
                          "frac": achieved / dgemm_tflops, "traffic": None,
-                         "note": "FP64 flops of the H_eff contractions (8 per complex MAC, dense W) / the WHOLE step time "
-                                 "(Lanczos vector work, SVD and QR included); peak = cuBLAS DGEMM 8192^3 measured in this run "
-                                 "(nominal B200 FP64 tensor peak: 40 TFLOP/s)"},
+                         "kernel": "qca::zgemm_dmma_kernel (L.psi and T.R contractions of H_eff, FP64 tensor cores)",
+                         "launches_per_step": zp["launches"], "avg_launch_ms": zp["ms"] / max(zp["launches"], 1),
+                         "kernel_share_of_step": zp["ms"] / (ms / args.tdvp_steps),
+                         "whole_step_tflops": whole, "whole_step_frac": whole / dgemm_tflops,
+                         "note": "achieved = FP64 operations of the DMMA launches of one time step (8 M N K per complex GEMM) / "
+                                 "their summed CUDA-event durations, measured live; whole_step_tflops = the same operations / "
+                                 "the WHOLE step time (Lanczos vector work, SVD, QR, environments included); peak = cuBLAS "
+                                 "DGEMM 8192^3 measured in this run (nominal B200 FP64 tensor peak: 40 TFLOP/s)"},
             "e2e": {"value": 2 * args.tdvp_steps / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 64 * n, "h2d_bytes_once": h2d,
                     "api": "TDVP.measure + TDVP.do_time_step (state resident on the device between steps, as in the reference's loop)"}}

@@ -97,6 +97,22 @@ typedef struct qca_remote_op {
 int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_op_t* ops,
                         int32_t capacity, int32_t* nops);
 
+/* How the fast tile-pass kernel spreads those terms over the passes of one operator application.
+ * Every launch has `nslots` remote operand slots; slot s of pass p carries, for the amplitudes x whose
+ * rotation is r, term op_of[p][s][r] of the qca_plan_remote list (-1: none), with
+ *   r(x) = (rot_word >> 2 * ((x_local >> rot_shift) & 15)) & 3  <  npasses.
+ * Each term is applied in exactly one pass for every x, and every pass pulls (nearly) the same share of
+ * every term over NVLink, so the NVLink time overlaps the HBM time of every launch.  (The `pass` field of
+ * qca_remote_op_t is the static placement the generic kernel uses instead.) */
+typedef struct qca_remote_rotation {
+    int32_t nslots;
+    int32_t npasses;
+    int32_t rot_shift;
+    uint32_t rot_word;
+    int32_t op_of[4][2][4];
+} qca_remote_rotation_t;
+int32_t qca_plan_rotation(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_rotation_t* out);
+
 /* ------------------------------------------------------------------------
  * Exact evolution engine == algorithms/exact.py:9-27 (class Exact).
  * ---------------------------------------------------------------------- */
@@ -174,6 +190,7 @@ typedef struct qca_exact_stats {
     uint64_t profiled_pass_launches;
     double device_bytes;         /* bytes of device memory held */
     double remote_bytes;         /* bytes read from partner ranks over NVLink by pass launches */
+    double profiled_ms_by_pass[4]; /* profiled_pass_ms split by tile pass (0: the contiguous first tile) */
 } qca_exact_stats_t;
 int32_t qca_exact_get_stats(qca_exact_t h, qca_exact_stats_t* out);
 int32_t qca_exact_reset_stats(qca_exact_t h);
@@ -198,6 +215,11 @@ int32_t qca_zgemm_batched(const void* a, const void* b, void* c, int32_t M, int3
                           int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, int32_t nsplit, int64_t c_ssplit,
                           void* stream);
 
+/* Per-launch timing of qca_zgemm_batched (including the launches qca_heff_* make): returns the summed
+ * CUDA-event duration (ms), the FP64 operations (8 M N K S G per launch) and the number of launches recorded
+ * since the last call, then switches recording on (enable != 0) or off.  Synchronises; not thread safe. */
+int32_t qca_zgemm_profile(int32_t enable, double* ms, double* flops, uint64_t* launches);
+
 /* ------------------------------------------------------------------------
  * Matrix-free effective Hamiltonian of TDVP and its Krylov exponential (csrc/qca_heff.cu).  Replaces
  * TDVP._assemble_H_eff / _evolve_A (algorithms/tdvp.py:299-310, 350-365: a dense (g dl dr)^2 matrix per
@@ -218,15 +240,22 @@ typedef struct qca_heff {
     const int32_t* mix_col;      /* [nnz] */
     const void* mix_val;         /* [nnz] complex128 */
     int32_t dl, dr, wl, wr, g;
+    /* structural zeros (HOST values; honoured when use_masks != 0 and wl, wr <= 32): col_mask[g] bit w set iff
+     * column (g, w) of Mx has an entry, row_mask[g'] bit n set iff row (g', n) has one.  Contractions that
+     * only feed unused columns or produce empty rows are skipped. */
+    int32_t use_masks;
+    uint32_t col_mask[4], row_mask[4];
 } qca_heff_t;
 int32_t qca_heff_workspace_bytes(const qca_heff_t* h, int32_t krylov_dim, uint64_t* bytes);
 /* out = H_eff psi */
 int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* workspace, uint64_t workspace_bytes,
                        void* stream);
 /* out = exp(-i t H_eff) psi by krylov_dim (<= 64) Lanczos steps with full re-orthogonalisation; the small
- * tridiagonal problem is solved on the device too (Jacobi).  out may alias psi. */
-int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t krylov_dim, double t, void* workspace,
-                      uint64_t workspace_bytes, void* stream);
+ * tridiagonal exponential is evaluated on the device too: a Chebyshev series when spectral_bound >= ||H_eff||
+ * is given (e.g. qca_spectral_bound of the rule, valid for environments built from isometries), Jacobi
+ * otherwise (spectral_bound = 0) or when the bound turns out too small.  out may alias psi. */
+int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t krylov_dim, double t, double spectral_bound,
+                      void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The state is sharded over the top

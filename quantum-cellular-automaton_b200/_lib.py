@@ -51,16 +51,24 @@ class ExactStats(C.Structure):
     _fields_ = [("spectral_bound", C.c_double), ("planes", C.c_int32), ("passes_per_apply", C.c_int32),
                 ("last_terms", C.c_int32), ("local_bits", C.c_int32), ("kernel_launches", C.c_uint64),
                 ("pass_launches", C.c_uint64), ("pass_bytes", C.c_double), ("profiled_pass_ms", C.c_double),
-                ("profiled_pass_launches", C.c_uint64), ("device_bytes", C.c_double), ("remote_bytes", C.c_double)]
+                ("profiled_pass_launches", C.c_uint64), ("device_bytes", C.c_double), ("remote_bytes", C.c_double),
+                ("profiled_ms_by_pass", C.c_double * 4)]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        out = {name: getattr(self, name) for name, _ in self._fields_}
+        out["profiled_ms_by_pass"] = list(self.profiled_ms_by_pass)
+        return out
+
+
+class RotationStruct(C.Structure):
+    _fields_ = [("nslots", C.c_int32), ("npasses", C.c_int32), ("rot_shift", C.c_int32), ("rot_word", C.c_uint32),
+                ("op_of", C.c_int32 * 32)]
 
 
 class HeffStruct(C.Structure):
     _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("mix_rowptr", C.c_void_p), ("mix_col", C.c_void_p),
                 ("mix_val", C.c_void_p), ("dl", C.c_int32), ("dr", C.c_int32), ("wl", C.c_int32), ("wr", C.c_int32),
-                ("g", C.c_int32)]
+                ("g", C.c_int32), ("use_masks", C.c_int32), ("col_mask", C.c_uint32 * 4), ("row_mask", C.c_uint32 * 4)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -76,6 +84,7 @@ SYMBOLS = {
     "qca_plan_shard": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_remote": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.c_int32, C.POINTER(RemoteOpStruct), C.c_int32,
                                     C.POINTER(C.c_int32)]),
+    "qca_plan_rotation": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.c_int32, C.POINTER(RotationStruct)]),
     "qca_exact_plane_flags": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qca_exact_resolve_planes": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "qca_exact_create": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(RuleStruct), C.c_int32, C.c_int32,
@@ -98,10 +107,11 @@ SYMBOLS = {
                                        C.c_void_p]),
     "qca_zgemm_batched": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 9
                           + [C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "qca_zgemm_profile": (C.c_int32, [C.c_int32, _dp, _dp, C.POINTER(C.c_uint64)]),
     "qca_heff_workspace_bytes": (C.c_int32, [C.POINTER(HeffStruct), C.c_int32, C.POINTER(C.c_uint64)]),
     "qca_heff_apply": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
-    "qca_heff_expm": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
-                                  C.c_uint64, C.c_void_p]),
+    "qca_heff_expm": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_uint64, C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
@@ -176,6 +186,22 @@ def plan_remote(rules, world_size: int, rank: int) -> list[dict]:
     check(lib.qca_plan_remote(C.byref(rs), world_size, rank, buf, max(n.value, 1), C.byref(n)))
     return [dict(pass_index=o.pass_, partner=o.partner, qubit=o.qubit, sign=o.sign, mask=o.mask, shift=o.shift,
                  window_bits=o.window_bits) for o in buf[:n.value]]
+
+
+def zgemm_profile(enable: bool) -> dict:
+    """Collect (and reset) the per-launch timings of the DMMA contraction kernel; see qca_zgemm_profile."""
+    ms, flops, n = C.c_double(), C.c_double(), C.c_uint64()
+    check(lib.qca_zgemm_profile(int(enable), C.byref(ms), C.byref(flops), C.byref(n)))
+    return {"ms": ms.value, "flops": flops.value, "launches": n.value}
+
+
+def plan_rotation(rules, world_size: int, rank: int) -> dict:
+    """How the fast kernel rotates the remote terms over the passes (qca_plan_rotation)."""
+    out = RotationStruct()
+    rs = rule_struct(rules)
+    check(lib.qca_plan_rotation(C.byref(rs), world_size, rank, C.byref(out)))
+    op_of = np.array(list(out.op_of), dtype=np.int64).reshape(4, 2, 4)
+    return dict(nslots=out.nslots, npasses=out.npasses, rot_shift=out.rot_shift, rot_word=out.rot_word, op_of=op_of)
 
 
 def plan_shard(rules, world_size: int) -> list[int]:

@@ -281,9 +281,10 @@ class TDVP(Algorithm):
         m = min(krylov_dimension(abs(t) * self._bound), dim)
         dl, dr = left.shape[0], right.shape[0]
         self.heff_applications += m
-        # FP64 operations of the two tensor-core contractions L.psi and T.R (8 per complex MAC)
-        self.heff_flops += m * 8.0 * op.g * (op.wl * dl * dl * dr + op.wr * dl * dr * dr)
-        return heff_expm(left, right, op, psi, m, t).reshape(psi.shape)
+        # FP64 operations of the two tensor-core contractions L.psi and T.R (8 per complex MAC); MPO channels
+        # that are structurally zero are neither computed nor counted
+        self.heff_flops += m * 8.0 * (op.cols_used * dl * dl * dr + op.rows_used * dl * dr * dr)
+        return heff_expm(left, right, op, psi, m, t, spectral_bound=self._bound).reshape(psi.shape)
 
     def _evolve_site(self, site, delta):
         left, right, w = self._env_left(site - 1), self._env_right(site + 1), self._W[site]

@@ -231,6 +231,8 @@ struct Engine {
     double bound = 0.0;   // spectral bound R
     std::vector<qca_pass_t> passes;
     std::vector<qca_remote_op_t> remote;
+    qca_remote_rotation_t rotation{};  // fast kernel: how the remote terms rotate over the passes
+    int remote_rows = 4;               // rows of the remote operand ring (QCA_REMOTE_RING=6: deeper, shallower local ring)
     double remote_fraction[64] = {};   // per sharded qubit (global bit): fraction of the plane its term reads
     double2* staging = nullptr;
     unsigned long long staging_amps = 0;
@@ -253,7 +255,8 @@ struct Engine {
     unsigned long long epoch = 0;
     // stats
     qca_exact_stats_t st{};
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    struct ProfiledLaunch { cudaEvent_t ev0, ev1; int pass; };
+    std::vector<ProfiledLaunch> prof;
 
     size_t plane_bytes() const { return (size_t)namps * sizeof(double); }
 };
@@ -373,13 +376,17 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     const bool wide = (e->rule.ncells > 31);
     PassKernel kern = nullptr;
     int nunc = 0;
-    while (nunc < a.nstreams && a.s[nunc].bit < 0) ++nunc;  // unconditional streams come first
-    if (e->fast_path && T == kTile && a.nstreams <= kMaxFastStreams)
-        kern = wide ? fast_pass_kernel_u64(ps.low_bits, nunc, a.nstreams - nunc)
-                    : fast_pass_kernel_u32(ps.low_bits, nunc, a.nstreams - nunc);
+    while (nunc < a.nstreams && a.s[nunc].bit < 0) ++nunc;  // local operands come first
+    if (e->fast_path && T == kTile && nunc == a.nstreams)   // remote terms travel in a.rs
+        kern = wide ? fast_pass_kernel_u64(ps.low_bits, nunc, a.nrem, e->remote_rows)
+                    : fast_pass_kernel_u32(ps.low_bits, nunc, a.nrem, e->remote_rows);
     const bool fast = kern != nullptr;
     if (fast) smem = kPassSmemBytes;
-    else kern = generic_pass_kernel(wide);
+    else {
+        QCA_REQUIRE(a.nrem == 0, QCA_ERR_UNSUPPORTED, "no fast tile-pass kernel for %d local operands and %d remote slots",
+                    nunc, a.nrem);
+        kern = generic_pass_kernel(wide);
+    }
     QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
     dim3 grid(gx, e->nplanes, 1);
@@ -393,7 +400,7 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     QCA_CUDA(cudaGetLastError());
     if (profile) {
         QCA_CUDA(cudaEventRecord(ev1, e->stream));
-        e->prof.emplace_back(ev0, ev1);
+        e->prof.push_back({ev0, ev1, (int)pass_index});
     }
     // algorithmic bytes: every LOCAL operand vector once per plane (remote operands travel over
     // NVLink and are accounted separately)
@@ -430,17 +437,36 @@ static int32_t apply_operator(Engine* e, int v_out, int v_in, int v_a, double al
         } else {
             add_local(v_out, 1.0);
         }
-        for (const qca_remote_op_t& op : e->remote) {
-            if (op.pass != (int)i) continue;
-            QCA_REQUIRE(ns < kMaxStreams, QCA_ERR_UNSUPPORTED, "too many remote terms in one pass");
-            EpiStream& st = a.s[ns++];
-            for (int p = 0; p < 2; ++p) st.ptr[p] = e->peer_plane[op.partner][v_in][p];
-            st.coef = gamma * (double)op.sign; st.mask = op.mask; st.shift = op.shift; st.bit = op.qubit;
+        if (e->fast_path && !e->remote.empty()) {
+            // fast kernel: every launch has the same remote slots; which term a slot carries at x
+            // follows the rotation of x (qca_plan_rotation)
+            const qca_remote_rotation_t& rot = e->rotation;
+            a.nrem = rot.nslots; a.rot_word = rot.rot_word; a.rot_shift = rot.rot_shift;
+            for (int sl = 0; sl < rot.nslots; ++sl)
+                for (int r = 0; r < rot.npasses; ++r) {
+                    const int j = rot.op_of[i][sl][r];
+                    if (j < 0) continue;
+                    const qca_remote_op_t& op = e->remote[j];
+                    RemoteAlt& al = a.rs[sl].alt[r];
+                    for (int p = 0; p < 2; ++p) al.ptr[p] = e->peer_plane[op.partner][v_in][p];
+                    al.coef = gamma * (double)op.sign; al.mask = op.mask; al.shift = op.shift;
+                }
+        } else {
+            for (const qca_remote_op_t& op : e->remote) {   // generic kernel: static placement
+                if (op.pass != (int)i) continue;
+                QCA_REQUIRE(ns < kMaxStreams, QCA_ERR_UNSUPPORTED, "too many remote terms in one pass");
+                EpiStream& st = a.s[ns++];
+                for (int p = 0; p < 2; ++p) st.ptr[p] = e->peer_plane[op.partner][v_in][p];
+                st.coef = gamma * (double)op.sign; st.mask = op.mask; st.shift = op.shift; st.bit = op.qubit;
+            }
         }
         a.nstreams = ns;
         a.gamma = gamma;
         QCA_CHECK(launch_pass(e, i, a));
     }
+    if (e->fast_path)   // (the generic path counts its remote streams per launch)
+        for (const qca_remote_op_t& op : e->remote)
+            e->st.remote_bytes += e->remote_fraction[op.qubit] * (double)e->plane_bytes() * e->nplanes;
     return QCA_OK;
 }
 
@@ -495,10 +521,11 @@ static int32_t finish_profile(Engine* e) {
     QCA_CUDA(cudaStreamSynchronize(e->stream));
     for (auto& pr : e->prof) {
         float ms = 0.f;
-        QCA_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        QCA_CUDA(cudaEventElapsedTime(&ms, pr.ev0, pr.ev1));
         e->st.profiled_pass_ms += ms;
         e->st.profiled_pass_launches += 1;
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        if (pr.pass >= 0 && pr.pass < 4) e->st.profiled_ms_by_pass[pr.pass] += ms;
+        cudaEventDestroy(pr.ev0); cudaEventDestroy(pr.ev1);
     }
     e->prof.clear();
     return QCA_OK;
@@ -814,6 +841,8 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     e->bound = qca::spectral_bound(*rule);
     qca::plan_passes(e->local_bits, e->passes);
     if (int32_t rc = qca::plan_remote(*rule, world_size, rank, e->remote)) { delete h; return rc; }
+    if (int32_t rc = qca::plan_rotation(*rule, world_size, rank, &e->rotation)) { delete h; return rc; }
+    if (const char* env = getenv("QCA_REMOTE_RING")) e->remote_rows = (atoi(env) == 6) ? 6 : 4;
     for (const qca_remote_op_t& op : e->remote)  // fraction of the plane the term reads on this rank
         e->remote_fraction[op.qubit] = op.window_bits <= 4
             ? (double)__builtin_popcount(op.mask & 0xffffu) / 16.0 : 1.0;   // the mask is replicated over 16 entries
@@ -863,7 +892,7 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     Engine* e = &h->e;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (auto& pr : e->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : e->prof) { cudaEventDestroy(pr.ev0); cudaEventDestroy(pr.ev1); }
     if (e->peers_ready) {
         for (int r = 0; r < e->world; ++r) {
             if (r == e->rank) continue;
@@ -1062,6 +1091,7 @@ int32_t qca_exact_reset_stats(qca_exact_t h) {
     Engine* e = &h->e;
     e->st.kernel_launches = 0; e->st.pass_launches = 0; e->st.pass_bytes = 0.0; e->st.remote_bytes = 0.0;
     e->st.profiled_pass_ms = 0.0; e->st.profiled_pass_launches = 0;
+    for (double& v : e->st.profiled_ms_by_pass) v = 0.0;
     return QCA_OK;
 }
 

@@ -20,7 +20,11 @@
 
 #include <algorithm>
 
+#include <vector>
+
 #include "qca_common.cuh"
+#include "qca_plan.h"
+#include "qca_zgemm.h"
 
 namespace qca {
 
@@ -146,14 +150,20 @@ he_update_kernel(double2* __restrict__ w, const double2* __restrict__ V, long lo
                  const double2* __restrict__ partial, int nparts, double* alpha_out, double* norm_partial) {
     __shared__ double2 c[HE_MAXK];
     __shared__ double red[8];
-    if (threadIdx.x < nvec) {
-        double cr = 0.0, ci = 0.0;
-        for (int b = 0; b < nparts; ++b) {
-            const double2 p = partial[(long long)b * HE_MAXK + threadIdx.x];
-            cr += p.x; ci += p.y;
+    {   // one warp per coefficient: lanes add the block partials in a fixed order, then a butterfly
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int i = warp; i < nvec; i += HE_THREADS / 32) {
+            double cr = 0.0, ci = 0.0;
+            for (int b = lane; b < nparts; b += 32) {
+                const double2 p = partial[(long long)b * HE_MAXK + i];
+                cr += p.x; ci += p.y;
+            }
+            cr = he_warp_sum(cr); ci = he_warp_sum(ci);
+            if (lane == 0) {
+                c[i] = make_double2(cr, ci);
+                if (alpha_out && blockIdx.x == 0 && i == nvec - 1) *alpha_out = cr;
+            }
         }
-        c[threadIdx.x] = make_double2(cr, ci);
-        if (alpha_out && blockIdx.x == 0 && threadIdx.x == nvec - 1) *alpha_out = cr;
     }
     __syncthreads();
     long long s0, s1;
@@ -177,12 +187,11 @@ he_update_kernel(double2* __restrict__ w, const double2* __restrict__ V, long lo
 }
 
 // alpha = Re sum_blocks partial[block][0]   (last Lanczos step: only the diagonal entry is needed)
-__global__ void he_alpha_kernel(const double2* __restrict__ partial, int nparts, double* alpha_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double cr = 0.0;
-        for (int b = 0; b < nparts; ++b) cr += partial[(long long)b * HE_MAXK].x;
-        *alpha_out = cr;
-    }
+__global__ void he_alpha_kernel(const double2* __restrict__ partial, int nparts, double* alpha_out) {   // <<<1, 32>>>
+    double cr = 0.0;   // same summation order as he_update_kernel
+    for (int b = threadIdx.x; b < nparts; b += 32) cr += partial[(long long)b * HE_MAXK].x;
+    cr = he_warp_sum(cr);
+    if (threadIdx.x == 0) *alpha_out = cr;
 }
 
 __global__ void __launch_bounds__(HE_THREADS)
@@ -226,15 +235,86 @@ he_normalize_kernel(double2* dst, const double2* src, long long dim,   // dst ma
     }
 }
 
-// coef = norm0 * Z exp(-i t Lambda) Z^T e_0 for the m x m Lanczos matrix T = tridiag(beta, alpha, beta)
-// (lautils.py:45-55 applied to T).  One warp, cyclic Jacobi in shared memory: unconditionally accurate
-// for the small, possibly decoupled (beta = 0) matrices that occur here.
+constexpr int HE_MAXCHEB = 200;
+struct ChebCoefs {
+    double a[HE_MAXCHEB];   // a_k = (2 - delta_k0) J_k(R |t|)
+    int n;                  // 0: no plan (bound unknown or too many terms)
+    double R;               // ||T|| <= R
+};
+
+// coef = norm0 * exp(-i t T) e_0 for the m x m Lanczos matrix T = tridiag(beta, alpha, beta)
+// (lautils.py:45-55 applied to T).  One warp.
+//  * Chebyshev path: with ||T|| <= ||H_eff|| <= R,  exp(-i t T) e_0 = sum_k a_k (-i sgn t)^k T_k(T/R) e_0
+//    (three-term recurrence on a real m-vector, a_k from the host's Bessel plan): a few dozen tridiagonal
+//    matrix-vector products, no divisions or square roots;
+//  * Jacobi path (no bound given, too many terms, or the Gershgorin radius of T exceeds R): cyclic Jacobi
+//    in shared memory, coef = norm0 * Z exp(-i t Lambda) Z^T e_0; unconditionally accurate for the small,
+//    possibly decoupled (beta = 0) matrices that occur here.
 __global__ void he_tridiag_expm_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int m,
-                                       const double* __restrict__ norm0, double t, double2* __restrict__ coef) {
+                                       const double* __restrict__ norm0, double t, double2* __restrict__ coef,
+                                       const ChebCoefs cheb) {
     extern __shared__ double jsm[];
     double* A = jsm;            // m x m
     double* Z = jsm + m * m;    // m x m, columns = eigenvectors
     const int lane = threadIdx.x;
+    if (cheb.n > 0) {
+        // rows i = lane and lane + 32 of T
+        double al[2], bl[2], bu[2];   // diagonal, coupling to i-1, coupling to i+1
+        double gersh = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            al[h] = i < m ? alpha[i] : 0.0;
+            bl[h] = (i < m && i > 0) ? beta[i] : 0.0;
+            bu[h] = (i + 1 < m) ? beta[i + 1] : 0.0;
+            gersh = fmax(gersh, fabs(al[h]) + fabs(bl[h]) + fabs(bu[h]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gersh = fmax(gersh, __shfl_xor_sync(0xffffffffu, gersh, o));
+        if (gersh <= cheb.R) {   // (uniform) the spectrum of T lies inside [-R, R]
+            double* u = jsm;     // current Chebyshev vector, with one zero on either side: u[1 + i]
+            const double inv = 1.0 / cheb.R;
+            const double sg = t < 0.0 ? -1.0 : 1.0;
+            for (int e = lane; e < m + 2; e += 32) u[e] = (e == 1) ? 1.0 : 0.0;
+            __syncwarp();
+            double prev[2] = {0.0, 0.0}, cur[2], re[2], im[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { cur[h] = (lane + 32 * h == 0) ? 1.0 : 0.0; re[h] = cheb.a[0] * cur[h]; }
+            for (int k = 1; k < cheb.n; ++k) {
+                double nxt[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h;
+                    double tv = 0.0;
+                    if (i < m) tv = (al[h] * u[1 + i] + bl[h] * u[i] + bu[h] * u[2 + i]) * inv;
+                    nxt[h] = (k == 1) ? tv : 2.0 * tv - prev[h];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h;
+                    if (i < m) u[1 + i] = nxt[h];
+                    prev[h] = cur[h]; cur[h] = nxt[h];
+                    // (-i sg)^k: 1, -i sg, -1, +i sg
+                    const double ak = cheb.a[k];
+                    switch (k & 3) {
+                        case 0: re[h] += ak * nxt[h]; break;
+                        case 1: im[h] -= sg * ak * nxt[h]; break;
+                        case 2: re[h] -= ak * nxt[h]; break;
+                        default: im[h] += sg * ak * nxt[h]; break;
+                    }
+                }
+                __syncwarp();
+            }
+            const double n0 = *norm0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if (i < m) coef[i] = make_double2(n0 * re[h], n0 * im[h]);
+            }
+            return;
+        }
+    }
     for (int e = lane; e < m * m; e += 32) {
         const int r = e / m, c = e % m;
         double v = 0.0;
@@ -254,12 +334,13 @@ __global__ void he_tridiag_expm_kernel(const double* __restrict__ alpha, const d
         }
         off = he_warp_sum(off);
         diag = he_warp_sum(diag);
-        if (off <= 1e-34 * diag || off == 0.0) break;
+        if (off <= 1e-31 * diag || off == 0.0) break;   // off-diagonal norm below 3e-16 of the matrix norm
         for (int p = 0; p < m - 1; ++p) {
             for (int q = p + 1; q < m; ++q) {
                 const double apq = A[p * m + q];
                 if (apq == 0.0) continue;       // uniform across the warp
                 const double app = A[p * m + p], aqq = A[q * m + q];
+                if (fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq))) continue;   // below the rounding of the diagonal
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
@@ -356,8 +437,19 @@ static int32_t he_plan(const qca_heff_t* h, int m, HeffPlan* p) {
     p->dim = p->plane * h->g;
     p->t1 = p->plane * h->g * h->wl;
     p->t3 = p->plane * h->g * h->wr;
-    p->ns1 = he_split((long long)h->wl * h->dl, h->dr, h->g, (h->dl + 15) / 16, p->sms);
-    p->ns2 = he_split(h->dl, h->dr, h->g, (long long)h->wr * ((h->dr + 15) / 16), p->sms);
+    // (with structural zeros: tiles / segments that are actually computed)
+    const bool masks = h->use_masks && h->wl <= 32 && h->wr <= 32;
+    int cols = h->g * h->wl, rows_max = h->wr;
+    if (masks) {
+        cols = 0; rows_max = 1;
+        for (int i = 0; i < h->g; ++i) {
+            cols += __builtin_popcount(h->col_mask[i]);
+            rows_max = std::max(rows_max, __builtin_popcount(h->row_mask[i]));
+        }
+        QCA_REQUIRE(cols >= 1, QCA_ERR_ARG, "site operator without any entry");
+    }
+    p->ns1 = he_split((long long)cols * h->dl, h->dr, 1, (h->dl + 15) / 16, p->sms);
+    p->ns2 = he_split(h->dl, h->dr, h->g, (long long)rows_max * ((h->dr + 15) / 16), p->sms);
     p->nblocks = (int)std::max<long long>(1, std::min<long long>((p->dim + 2 * HE_THREADS - 1) / (2 * HE_THREADS), 2ll * p->sms));
     long long o = 0;
     p->off_t1 = o; o += p->t1 * p->ns1;
@@ -376,16 +468,39 @@ static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* p
     double2* t3 = ws + p.off_t3;
     double2* p2 = ws + p.off_p2;
     const int dl = h->dl, dr = h->dr, wl = h->wl, wr = h->wr, g = h->g;
+    // structural zeros of the site operator(s): channels (g, w) of T1 nobody reads, channels (g', n) of T3
+    // that are identically zero (two thirds of the work remain for the automaton's MPO)
+    const bool masks = h->use_masks && wl <= 32 && wr <= 32;
     // T1[g][w][y][u] = sum_x L[x][(w,y)] psi[g][x][u]
-    QCA_CHECK(qca_zgemm_batched(h->left, psi, t1, wl * dl, dr, dl, 1, g, 0, 0, 1, (int64_t)wl * dl, (int64_t)dl * dr, 0, dr,
-                                (int64_t)wl * dl * dr, dr, 0, p.ns1, p.t1, st));
+    ZgemmArgs z{};
+    z.a = (const double2*)h->left; z.b = psi; z.c = t1;
+    z.M = wl * dl; z.N = dr; z.K = dl; z.S = 1; z.G = g;
+    z.a_sg = 0; z.a_ss = 0; z.a_sm = 1; z.a_sk = (long long)wl * dl;
+    z.b_sg = (long long)dl * dr; z.b_ss = 0; z.b_sk = dr;
+    z.c_sg = (long long)wl * dl * dr; z.c_sm = dr;
+    z.nsplit = p.ns1; z.c_ssplit = p.t1;
+    if (masks) {
+        z.use_masks = 1; z.chan_len = dl;
+        for (int i = 0; i < g; ++i) { z.chan_mask[i] = h->col_mask[i]; z.seg_mask[i] = 1u; }
+    }
+    QCA_CHECK(zgemm_launch(z, st));
     const int mix_blocks = (int)std::max<long long>(1, std::min<long long>((p.plane + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
     he_mix_kernel<<<mix_blocks, HE_THREADS, 0, st>>>(t1, p.ns1, p.t1, t3, h->mix_rowptr, h->mix_col, (const double2*)h->mix_val,
                                                      g * wr, p.plane);
     QCA_CUDA(cudaGetLastError());
     // out[g][y][v] = sum_n sum_u T3[g][n][y][u] R[u][n][v]
-    QCA_CHECK(qca_zgemm_batched(t3, h->right, p2, dl, dr, dr, wr, g, (int64_t)wr * dl * dr, (int64_t)dl * dr, dr, 1, 0, dr,
-                                (int64_t)wr * dr, (int64_t)dl * dr, dr, 0, p.ns2, p.dim, st));
+    ZgemmArgs y{};
+    y.a = t3; y.b = (const double2*)h->right; y.c = p2;
+    y.M = dl; y.N = dr; y.K = dr; y.S = wr; y.G = g;
+    y.a_sg = (long long)wr * dl * dr; y.a_ss = (long long)dl * dr; y.a_sm = dr; y.a_sk = 1;
+    y.b_sg = 0; y.b_ss = dr; y.b_sk = (long long)wr * dr;
+    y.c_sg = (long long)dl * dr; y.c_sm = dr;
+    y.nsplit = p.ns2; y.c_ssplit = p.dim;
+    if (masks) {
+        y.use_masks = 1; y.chan_len = dl;
+        for (int i = 0; i < g; ++i) { y.chan_mask[i] = 1u; y.seg_mask[i] = h->row_mask[i]; }
+    }
+    QCA_CHECK(zgemm_launch(y, st));
     return QCA_OK;
 }
 
@@ -416,8 +531,8 @@ int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* wo
     return QCA_OK;
 }
 
-int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t m, double t, void* workspace,
-                      uint64_t workspace_bytes, void* stream) {
+int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t m, double t, double spectral_bound,
+                      void* workspace, uint64_t workspace_bytes, void* stream) {
     using namespace qca;
     QCA_REQUIRE(psi && out && workspace, QCA_ERR_ARG, "NULL argument");
     QCA_REQUIRE(m >= 1, QCA_ERR_ARG, "Krylov dimension must be >= 1");
@@ -457,10 +572,20 @@ int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t m
         }
         QCA_CUDA(cudaGetLastError());
     }
-    const int jsm = 2 * m * m * (int)sizeof(double);
+    ChebCoefs cheb{};
+    if (spectral_bound > 0.0) {
+        std::vector<double> a;
+        QCA_CHECK(chebyshev_plan(spectral_bound * fabs(t), 1e-17, a));
+        if ((int)a.size() <= HE_MAXCHEB) {
+            cheb.n = (int)a.size();
+            cheb.R = spectral_bound;
+            std::copy(a.begin(), a.end(), cheb.a);
+        }
+    }
+    const int jsm = std::max(2 * m * m, m + 2) * (int)sizeof(double);
     if (jsm > 48 * 1024)
         QCA_CUDA(cudaFuncSetAttribute(he_tridiag_expm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jsm));
-    he_tridiag_expm_kernel<<<1, 32, jsm, st>>>(alpha, beta, m, norm0, t, coef);
+    he_tridiag_expm_kernel<<<1, 32, jsm, st>>>(alpha, beta, m, norm0, t, coef, cheb);
     const int blocks = (int)std::max<long long>(1, std::min<long long>((p.dim + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
     he_combine_kernel<<<blocks, HE_THREADS, 0, st>>>((double2*)out, V, p.dim, m, coef);
     QCA_CUDA(cudaGetLastError());

@@ -206,22 +206,24 @@ constexpr int kPassWarps = kPassThreads / 32;
 constexpr int kPassMbarBytes = kPassWarps * 8 * 8;  // up to 8 mbarriers per warp (slots x rows)
 constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16 + kPassMbarBytes;  // 112.5 KiB: 2 CTAs/SM
 
-// ring depth (rows of look-ahead) of a local / a remote operand
-__host__ __device__ constexpr int ring_unc(int nunc, int nrem) {
-    return nunc == 0 ? 0 : (nrem == 0 ? kRingRowsTotal / nunc : (nunc == 1 ? 4 : (nrem == 1 ? 3 : 2)));
+// ring depth (rows of look-ahead) of a remote / a local operand.  HBM needs the deeper ring (measured:
+// a 4-row local ring costs 25 % of the pass bandwidth); the remote ring covers the NVLink latency with
+// RD rows (4, or 6 with one slot: QCA_REMOTE_RING=6) because its rows complete independently.
+__host__ __device__ constexpr int ring_rem(int nrem, int rd) {
+    return nrem == 0 ? 0 : (nrem == 1 ? rd : 4);
 }
-__host__ __device__ constexpr int ring_rem(int nunc, int nrem) {
-    return nrem == 0 ? 0 : (nunc == 2 ? (nrem == 1 ? 6 : 4) : (nrem == 1 ? 8 : 4));
+__host__ __device__ constexpr int ring_unc(int nunc, int nrem, int rd) {
+    return nunc == 0 ? 0 : (kRingRowsTotal - nrem * ring_rem(nrem, rd)) / nunc;
 }
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
 // FLIP_LOW: pass 0 (M == 0, L == 13): every local bit is flipped.  Otherwise only the M high bits are.
 // NUNC local epilogue operands (recurrence vectors), NREM remote slots (terms of sharded qubits).
-template <typename I, int L, bool FLIP_LOW, int NUNC, int NREM>
+template <typename I, int L, bool FLIP_LOW, int NUNC, int NREM, int RD = 4>
 __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs a) {
     constexpr int M = kTile - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;  // first flipped local bit
-    constexpr int DU = ring_unc(NUNC, NREM), DC = ring_rem(NUNC, NREM);   // look-ahead per operand kind
+    constexpr int DU = ring_unc(NUNC, NREM, RD), DC = ring_rem(NREM, RD);   // look-ahead per operand kind
     constexpr int CHUNK_LANES = (L >= 6) ? 32 : (1 << (L - 1));  // lanes whose pairs are contiguous in global memory
     constexpr int ISSUERS = 32 / CHUNK_LANES;                    // bulk copies per warp and row
     static_assert(NUNC * DU + NREM * DC <= kRingRowsTotal, "ring budget");
@@ -422,8 +424,8 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
 
 // kernel tables, one translation unit per index type (qca_pass_u32.cu / qca_pass_u64.cu)
 typedef void (*PassKernel)(const PassArgs);
-PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int nrem);
-PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int nrem);
+PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int nrem, int remote_rows);
+PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int nrem, int remote_rows);
 PassKernel generic_pass_kernel(bool wide);
 
 }  // namespace qca

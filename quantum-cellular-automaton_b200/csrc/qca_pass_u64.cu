@@ -3,38 +3,42 @@
 
 namespace qca {
 
-// later passes: one recurrence operand (c = out) plus up to three remote terms
+// later passes: one recurrence operand (c = out) plus up to two remote slots
 template <int L>
-static PassKernel later_pass(int nunc, int ncond) {
+static PassKernel later_pass(int nunc, int nrem, int rd) {
     if (nunc != 1) return nullptr;
-    switch (ncond) {
+    if (nrem == 1 && rd == 6) return pass_kernel_v2<unsigned long long, L, false, 1, 1, 6>;
+    switch (nrem) {
         case 0: return pass_kernel_v2<unsigned long long, L, false, 1, 0>;
         case 1: return pass_kernel_v2<unsigned long long, L, false, 1, 1>;
         case 2: return pass_kernel_v2<unsigned long long, L, false, 1, 2>;
-        case 3: return pass_kernel_v2<unsigned long long, L, false, 1, 3>;
         default: return nullptr;
     }
 }
 
-PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int ncond) {
+PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int nrem, int rd) {
     switch (low_bits) {
-        case 13:  // pass 0: no operand (test hook) or both recurrence operands, at most one remote term
-            if (nunc == 0 && ncond == 0) return pass_kernel_v2<unsigned long long, 13, true, 0, 0>;
-            if (nunc == 0 && ncond == 1) return pass_kernel_v2<unsigned long long, 13, true, 0, 1>;
-            if (nunc == 1 && ncond == 0) return pass_kernel_v2<unsigned long long, 13, true, 1, 0>;
-            if (nunc == 1 && ncond == 1) return pass_kernel_v2<unsigned long long, 13, true, 1, 1>;
-            if (nunc == 2 && ncond == 0) return pass_kernel_v2<unsigned long long, 13, true, 2, 0>;
-            if (nunc == 2 && ncond == 1) return pass_kernel_v2<unsigned long long, 13, true, 2, 1>;
+        case 13:  // pass 0: no operand (test hook) or one / both recurrence operands, up to two remote slots
+            if (nunc == 2 && nrem == 1 && rd == 6) return pass_kernel_v2<unsigned long long, 13, true, 2, 1, 6>;
+            if (nunc == 0 && nrem == 0) return pass_kernel_v2<unsigned long long, 13, true, 0, 0>;
+            if (nunc == 0 && nrem == 1) return pass_kernel_v2<unsigned long long, 13, true, 0, 1>;
+            if (nunc == 0 && nrem == 2) return pass_kernel_v2<unsigned long long, 13, true, 0, 2>;
+            if (nunc == 1 && nrem == 0) return pass_kernel_v2<unsigned long long, 13, true, 1, 0>;
+            if (nunc == 1 && nrem == 1) return pass_kernel_v2<unsigned long long, 13, true, 1, 1>;
+            if (nunc == 1 && nrem == 2) return pass_kernel_v2<unsigned long long, 13, true, 1, 2>;
+            if (nunc == 2 && nrem == 0) return pass_kernel_v2<unsigned long long, 13, true, 2, 0>;
+            if (nunc == 2 && nrem == 1) return pass_kernel_v2<unsigned long long, 13, true, 2, 1>;
+            if (nunc == 2 && nrem == 2) return pass_kernel_v2<unsigned long long, 13, true, 2, 2>;
             return nullptr;
-        case 12: return later_pass<12>(nunc, ncond);
-        case 11: return later_pass<11>(nunc, ncond);
-        case 10: return later_pass<10>(nunc, ncond);
-        case 9: return later_pass<9>(nunc, ncond);
-        case 8: return later_pass<8>(nunc, ncond);
-        case 7: return later_pass<7>(nunc, ncond);
-        case 6: return later_pass<6>(nunc, ncond);
-        case 5: return later_pass<5>(nunc, ncond);
-        case 4: return later_pass<4>(nunc, ncond);
+        case 12: return later_pass<12>(nunc, nrem, rd);
+        case 11: return later_pass<11>(nunc, nrem, rd);
+        case 10: return later_pass<10>(nunc, nrem, rd);
+        case 9: return later_pass<9>(nunc, nrem, rd);
+        case 8: return later_pass<8>(nunc, nrem, rd);
+        case 7: return later_pass<7>(nunc, nrem, rd);
+        case 6: return later_pass<6>(nunc, nrem, rd);
+        case 5: return later_pass<5>(nunc, nrem, rd);
+        case 4: return later_pass<4>(nunc, nrem, rd);
         default: return nullptr;
     }
 }

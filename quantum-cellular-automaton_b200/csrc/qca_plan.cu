@@ -216,6 +216,30 @@ int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_re
     return QCA_OK;
 }
 
+// Rotation of the remote terms over the passes (fast kernel).  Term j goes to pass (j + r) mod npasses,
+// slot j / npasses, for the amplitudes of rotation r; r is read from four local index bits just above
+// the first tile (they are constant over every contiguous piece the kernel copies, and no term's
+// predicate depends on them for the registers that matter, so each pass gets ~1/npasses of every term).
+int32_t plan_rotation(const qca_rule_t& r, int world, int rank, qca_remote_rotation_t* out) {
+    *out = qca_remote_rotation_t{};
+    for (auto& p : out->op_of) for (auto& s : p) for (int& v : s) v = -1;
+    std::vector<qca_remote_op_t> ops;
+    QCA_CHECK(plan_remote(r, world, rank, ops));
+    int rank_bits = 0;
+    while ((1 << rank_bits) < world) ++rank_bits;
+    std::vector<qca_pass_t> passes;
+    plan_passes(r.ncells - rank_bits, passes);
+    const int np = (int)std::min<size_t>(passes.size(), 4);
+    out->npasses = np;
+    out->rot_shift = kTileBits;
+    for (unsigned v = 0; v < 16; ++v) out->rot_word |= (v % (unsigned)np) << (2 * v);
+    out->nslots = ((int)ops.size() + np - 1) / np;
+    QCA_REQUIRE(out->nslots <= 2, QCA_ERR_UNSUPPORTED, "%zu remote terms over %d passes", ops.size(), np);
+    for (int j = 0; j < (int)ops.size(); ++j)
+        for (int rot = 0; rot < np; ++rot) out->op_of[(j + rot) % np][j / np][rot] = j;
+    return QCA_OK;
+}
+
 }  // namespace qca
 
 extern "C" {
@@ -265,6 +289,14 @@ int32_t qca_plan_shard(const qca_rule_t* rule, int32_t world_size, int32_t* posi
     qca::plan_shard(*rule, world_size, &map, 0);
     for (int j = 0; j < map.nins; ++j) positions[j] = map.pos[j];
     return QCA_OK;
+}
+
+int32_t qca_plan_rotation(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_rotation_t* out) {
+    QCA_REQUIRE(rule && out, QCA_ERR_ARG, "NULL argument");
+    QCA_CHECK(qca::validate_rule(rule));
+    QCA_REQUIRE(world_size == 1 || world_size == 2 || world_size == 4 || world_size == 8, QCA_ERR_ARG, "bad world size");
+    QCA_REQUIRE(rank >= 0 && rank < world_size, QCA_ERR_ARG, "bad rank");
+    return qca::plan_rotation(*rule, world_size, rank, out);
 }
 
 int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank, qca_remote_op_t* ops,

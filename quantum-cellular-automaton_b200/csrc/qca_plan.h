@@ -20,5 +20,6 @@ void plan_passes(int local_bits, std::vector<qca_pass_t>& out);
 struct ShardMap;
 void plan_shard(const qca_rule_t& r, int world, ShardMap* map, int rank);
 int32_t plan_remote(const qca_rule_t& r, int world, int rank, std::vector<qca_remote_op_t>& out);
+int32_t plan_rotation(const qca_rule_t& r, int world, int rank, qca_remote_rotation_t* out);
 
 }  // namespace qca

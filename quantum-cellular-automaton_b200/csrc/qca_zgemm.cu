@@ -19,7 +19,11 @@
 // conflict free: the 8 lanes of a quarter-warp touch 8 distinct 16-byte slots of a 128-byte window.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "qca_common.cuh"
+#include "qca_zgemm.h"
 
 namespace qca {
 
@@ -33,16 +37,6 @@ constexpr int ZG_B_ELEMS = ZG_TK * ZG_B_LD;
 constexpr int ZG_STAGE_ELEMS = ZG_A_ELEMS + ZG_B_ELEMS;
 constexpr int ZG_SMEM_BYTES = ZG_STAGES * ZG_STAGE_ELEMS * 16;
 
-struct ZgemmArgs {
-    const double2* a; const double2* b; double2* c;
-    long long a_sg, a_ss, a_sm, a_sk;
-    long long b_sg, b_ss, b_sk;
-    long long c_sg, c_sm;
-    int M, N, K, S, G;
-    int conj_a;   // use conj(A)
-    int nsplit;   // split-K: blockIdx.z = g * nsplit + split; partial sums go to c + split * c_ssplit
-    long long c_ssplit;
-};
 
 __device__ __forceinline__ void zg_cp_async16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -64,15 +58,28 @@ __global__ void __launch_bounds__(ZG_THREADS, 2) zgemm_dmma_kernel(const ZgemmAr
     const int g = blockIdx.z / p.nsplit, split = blockIdx.z % p.nsplit;
     const double2* ag = p.a + (long long)g * p.a_sg;
     const double2* bg = p.b + (long long)g * p.b_sg;
+    unsigned smask = 0xffffffffu;
+    int nseg = p.S;
+    if (p.use_masks) {
+        const unsigned cm = p.chan_mask[g];
+        const int c0 = m0 / p.chan_len, c1 = min(m0 + ZG_TM - 1, p.M - 1) / p.chan_len;
+        bool any = false;
+        for (int c = c0; c <= c1; ++c) any |= (cm >> c) & 1u;
+        if (!any) return;                              // (uniform over the CTA)
+        smask = p.seg_mask[g];
+        nseg = __popc(smask);
+    }
     const int ktiles = (p.K + ZG_TK - 1) / ZG_TK;
-    const int all_steps = ktiles * p.S;                // pipeline steps: (segment, k-tile)
+    const int all_steps = ktiles * nseg;               // pipeline steps: (segment, k-tile)
     const int first = (int)((long long)all_steps * split / p.nsplit);
     const int total = (int)((long long)all_steps * (split + 1) / p.nsplit) - first;   // this CTA's share
 
     auto load_stage = [&](int step, int stage) {
         double2* sa = zsm + stage * ZG_STAGE_ELEMS;
         double2* sb = sa + ZG_A_ELEMS;
-        const int s = (first + step) / ktiles, k0 = ((first + step) % ktiles) * ZG_TK;
+        int s = (first + step) / ktiles;
+        const int k0 = ((first + step) % ktiles) * ZG_TK;
+        if (p.use_masks) s = __fns(smask, 0, s + 1);     // s-th used segment
         const double2* as = ag + (long long)s * p.a_ss;
         const double2* bs = bg + (long long)s * p.b_ss;
         // A tile: 64 x 16 complex = 1024 elements, 4 per thread
@@ -165,30 +172,92 @@ __global__ void __launch_bounds__(ZG_THREADS, 2) zgemm_dmma_kernel(const ZgemmAr
         }
 }
 
+// Optional per-launch timing (bench.py's roofline of the contraction kernel): an event pair around
+// every launch while enabled; single-threaded use.
+struct ZgemmProfile {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    double flops = 0.0;
+};
+static ZgemmProfile g_zprof;
+
 }  // namespace qca
 
 extern "C" {
+
+int32_t qca_zgemm_profile(int32_t enable, double* ms, double* flops, uint64_t* launches) {
+    qca::ZgemmProfile& pr = qca::g_zprof;
+    double total = 0.0;
+    for (auto& ev : pr.events) {
+        QCA_CUDA(cudaEventSynchronize(ev.second));
+        float t = 0.f;
+        QCA_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
+        total += t;
+        cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    if (ms) *ms = total;
+    if (flops) *flops = pr.flops;
+    if (launches) *launches = pr.events.size();
+    pr.events.clear();
+    pr.flops = 0.0;
+    pr.on = enable != 0;
+    return QCA_OK;
+}
 
 int32_t qca_zgemm_batched(const void* a, const void* b, void* c, int32_t M, int32_t N, int32_t K, int32_t S, int32_t G,
                           int64_t a_sg, int64_t a_ss, int64_t a_sm, int64_t a_sk, int64_t b_sg, int64_t b_ss,
                           int64_t b_sk, int64_t c_sg, int64_t c_sm, int32_t conj_a, int32_t nsplit, int64_t c_ssplit,
                           void* stream) {
-    QCA_REQUIRE(a && b && c, QCA_ERR_ARG, "NULL argument");
-    QCA_REQUIRE(M >= 1 && N >= 1 && K >= 1 && S >= 1 && G >= 1 && G <= 65535, QCA_ERR_ARG, "bad GEMM shape");
-    QCA_REQUIRE(a_sm == 1 || a_sk == 1, QCA_ERR_ARG, "A needs a unit stride in m or in k");
-    QCA_REQUIRE(nsplit >= 1 && (long long)G * nsplit <= 65535, QCA_ERR_ARG, "bad split count %d", nsplit);
     qca::ZgemmArgs p{};
     p.a = (const double2*)a; p.b = (const double2*)b; p.c = (double2*)c;
     p.a_sg = a_sg; p.a_ss = a_ss; p.a_sm = a_sm; p.a_sk = a_sk;
     p.b_sg = b_sg; p.b_ss = b_ss; p.b_sk = b_sk; p.c_sg = c_sg; p.c_sm = c_sm;
     p.M = M; p.N = N; p.K = K; p.S = S; p.G = G; p.conj_a = conj_a; p.nsplit = nsplit; p.c_ssplit = c_ssplit;
-    const dim3 grid((N + qca::ZG_TN - 1) / qca::ZG_TN, (M + qca::ZG_TM - 1) / qca::ZG_TM, G * nsplit);
-    // k contiguous in global memory: stage A as [m][k]; otherwise (m contiguous) as [k][m]
-    auto kern = (a_sk == 1 && a_sm != 1) ? qca::zgemm_dmma_kernel<true> : qca::zgemm_dmma_kernel<false>;
-    QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, qca::ZG_SMEM_BYTES));
-    kern<<<grid, qca::ZG_THREADS, qca::ZG_SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    QCA_CUDA(cudaGetLastError());
-    return QCA_OK;
+    return qca::zgemm_launch(p, (cudaStream_t)stream);
 }
 
 }  // extern "C"
+
+namespace qca {
+
+int32_t zgemm_launch(const ZgemmArgs& p, cudaStream_t stream) {
+    QCA_REQUIRE(p.a && p.b && p.c, QCA_ERR_ARG, "NULL argument");
+    QCA_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1 && p.S >= 1 && p.G >= 1 && p.G <= 65535, QCA_ERR_ARG, "bad GEMM shape");
+    QCA_REQUIRE(p.a_sm == 1 || p.a_sk == 1, QCA_ERR_ARG, "A needs a unit stride in m or in k");
+    QCA_REQUIRE(p.nsplit >= 1 && (long long)p.G * p.nsplit <= 65535, QCA_ERR_ARG, "bad split count %d", p.nsplit);
+    if (p.use_masks)
+        QCA_REQUIRE(p.G <= 4 && p.S <= 32 && p.chan_len >= 1 && (p.M + p.chan_len - 1) / p.chan_len <= 32, QCA_ERR_ARG,
+                    "masks need G <= 4, S <= 32 and at most 32 channels");
+    const dim3 grid((p.N + ZG_TN - 1) / ZG_TN, (p.M + ZG_TM - 1) / ZG_TM, p.G * p.nsplit);
+    // k contiguous in global memory: stage A as [m][k]; otherwise (m contiguous) as [k][m]
+    auto kern = (p.a_sk == 1 && p.a_sm != 1) ? zgemm_dmma_kernel<true> : zgemm_dmma_kernel<false>;
+    QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZG_SMEM_BYTES));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_zprof.on) {
+        QCA_CUDA(cudaEventCreate(&ev0)); QCA_CUDA(cudaEventCreate(&ev1));
+        QCA_CUDA(cudaEventRecord(ev0, stream));
+    }
+    kern<<<grid, ZG_THREADS, ZG_SMEM_BYTES, stream>>>(p);
+    QCA_CUDA(cudaGetLastError());
+    if (g_zprof.on) {
+        QCA_CUDA(cudaEventRecord(ev1, stream));
+        g_zprof.events.emplace_back(ev0, ev1);
+        // FP64 operations actually executed: 8 per complex multiply-add, skipped tiles / segments not counted
+        double rows_segs = 0.0;
+        for (int g = 0; g < p.G; ++g) {
+            if (!p.use_masks) { rows_segs += (double)p.M * p.S; continue; }
+            double rows = 0.0;
+            for (int m0 = 0; m0 < p.M; m0 += ZG_TM) {
+                const int c0 = m0 / p.chan_len, c1 = std::min(m0 + ZG_TM - 1, p.M - 1) / p.chan_len;
+                bool any = false;
+                for (int c = c0; c <= c1; ++c) any |= (p.chan_mask[g] >> c) & 1u;
+                if (any) rows += std::min(ZG_TM, p.M - m0);
+            }
+            rows_segs += rows * __builtin_popcount(p.seg_mask[g]);
+        }
+        g_zprof.flops += 8.0 * rows_segs * p.N * p.K;
+    }
+    return QCA_OK;
+}
+
+}  // namespace qca

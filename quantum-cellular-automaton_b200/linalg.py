@@ -189,6 +189,17 @@ class SiteOperator:
         self.rowptr = torch.as_tensor(rowptr, device=device)
         self.col = torch.as_tensor(col, device=device)
         self.val = torch.as_tensor(val, device=device)
+        # structural zeros: used columns (g, w) and non-empty rows (g', n), as bit masks per g
+        nnz = int(rowptr[-1])
+        self.col_mask, self.row_mask = [0] * 4, [0] * 4
+        for c in col[:nnz]:
+            self.col_mask[int(c) // self.wl] |= 1 << (int(c) % self.wl)
+        for r in range(self.g * self.wr):
+            if rowptr[r + 1] > rowptr[r]:
+                self.row_mask[r // self.wr] |= 1 << (r % self.wr)
+        self.use_masks = self.wl <= 32 and self.wr <= 32
+        self.cols_used = sum(bin(m).count("1") for m in self.col_mask) if self.use_masks else self.g * self.wl
+        self.rows_used = sum(bin(m).count("1") for m in self.row_mask) if self.use_masks else self.g * self.wr
 
 
 class _Workspace:
@@ -214,7 +225,8 @@ def _heff_struct(left, right, op: SiteOperator):
     assert dl == dl2 and dr == dr2 and wl == op.wl and wr == op.wr, (left.shape, right.shape, op.wl, op.wr)
     left, right = left.contiguous(), right.contiguous()
     h = _lib.HeffStruct(left.data_ptr(), right.data_ptr(), op.rowptr.data_ptr(), op.col.data_ptr(), op.val.data_ptr(),
-                        dl, dr, wl, wr, op.g)
+                        dl, dr, wl, wr, op.g, int(op.use_masks), (C.c_uint32 * 4)(*op.col_mask),
+                        (C.c_uint32 * 4)(*op.row_mask))
     return h, (left, right)   # keep the contiguous copies alive until the launches are enqueued
 
 
@@ -234,8 +246,9 @@ def heff_apply(left, right, op: SiteOperator, psi):
     return out
 
 
-def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float):
-    """exp(-i t H_eff) psi by `krylov_dim` Lanczos steps, all on the device, no host synchronisation."""
+def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float, spectral_bound: float = 0.0):
+    """exp(-i t H_eff) psi by `krylov_dim` Lanczos steps, all on the device, no host synchronisation.
+    spectral_bound: a bound of ||H_eff|| if known (the small exponential then is a Chebyshev series)."""
     import torch
     h, keep = _heff_struct(left, right, op)
     psi_c = psi.contiguous()
@@ -246,6 +259,6 @@ def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float):
     out = torch.empty_like(psi_c)
     stream = torch.cuda.current_stream(psi.device).cuda_stream
     _lib.check(_lib.lib.qca_heff_expm(C.byref(h), C.c_void_p(psi_c.data_ptr()), C.c_void_p(out.data_ptr()),
-                                      int(krylov_dim), float(t), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                      int(krylov_dim), float(t), float(spectral_bound), C.c_void_p(ws.data_ptr()), ws.numel(),
                                       C.c_void_p(stream)))
     return out

@@ -81,6 +81,64 @@ def test_remote_plan_reproduces_operator(world, n, d, lo, hi):
         assert max(loads) - min(loads) < 1e-12
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("n,d,lo,hi", [(17, 2, 2, 4), (19, 1, 1, 2), (22, 2, 2, 4), (24, 2, 1, 3), (30, 2, 2, 4), (33, 2, 2, 4)])
+def test_rotation_applies_every_remote_term_exactly_once(world, n, d, lo, hi):
+    """Fast-kernel placement (qca_plan_rotation): over the passes of one application every remote term
+    is carried by exactly one (pass, slot) for every rotation value, no slot carries two terms, and --
+    for the registers that matter -- every pass pulls the same share of every term."""
+    rules = RuleNS(n, d, lo, hi)
+    rbits = world.bit_length() - 1
+    nl = n - rbits
+    passes = _lib.plan_passes(nl)
+    if nl < 13 or len(passes) < 2:
+        pytest.skip("generic kernel regime")
+    for rank in range(world):
+        ops = _lib.plan_remote(rules, world, rank)
+        rot = _lib.plan_rotation(rules, world, rank)
+        assert rot["npasses"] == min(len(passes), 4) and rot["rot_shift"] == 13
+        assert rot["nslots"] == -(-len(ops) // rot["npasses"]) <= 2
+        rots = [(rot["rot_word"] >> (2 * v)) & 3 for v in range(16)]
+        assert max(rots) < rot["npasses"]
+        counts = np.bincount(rots, minlength=rot["npasses"])
+        assert counts.max() - counts.min() <= 1                       # rotations equally frequent
+        op_of = rot["op_of"]
+        for r in range(rot["npasses"]):
+            carried = [op_of[p, s, r] for p in range(rot["npasses"]) for s in range(rot["nslots"]) if op_of[p, s, r] >= 0]
+            assert sorted(carried) == list(range(len(ops)))           # every term exactly once
+        assert (op_of[rot["npasses"]:] == -1).all() and (op_of[:, rot["nslots"]:] == -1).all()
+        # share of term j carried by pass p = fraction of rotation values that send it there
+        for j in range(len(ops)):
+            share = [sum(counts[r] for r in range(rot["npasses"]) if j in op_of[p, :, r]) / 16.0 for p in range(rot["npasses"])]
+            assert abs(sum(share) - 1.0) < 1e-12 and max(share) - min(share) <= 1 / 16 + 1e-12
+    if n <= 22:   # numerically, on the full operator: rotation-placed terms == static placement
+        positions = _lib.plan_shard(rules, world)
+        rng = np.random.default_rng(n)
+        vec = rng.standard_normal(1 << n)
+        xl = np.arange(1 << nl, dtype=np.int64)
+        for rank in range(world):
+            ops = _lib.plan_remote(rules, world, rank)
+            rot = _lib.plan_rotation(rules, world, rank)
+            r_of_x = (rot["rot_word"] >> (2 * ((xl >> rot["rot_shift"]) & 15))) & 3
+            want = np.zeros(1 << nl)
+            got = np.zeros(1 << nl)
+            for op in ops:
+                partner = vec[sharding.local_indices(n, positions, op["partner"])]
+                on = ((op["mask"] >> ((xl >> op["shift"]) & 15)) & 1).astype(bool)
+                want[on] += op["sign"] * partner[on]
+            for p in range(rot["npasses"]):
+                for s_ in range(rot["nslots"]):
+                    for r in range(rot["npasses"]):
+                        j = rot["op_of"][p, s_, r]
+                        if j < 0:
+                            continue
+                        op = ops[j]
+                        partner = vec[sharding.local_indices(n, positions, op["partner"])]
+                        on = ((op["mask"] >> ((xl >> op["shift"]) & 15)) & 1).astype(bool) & (r_of_x == r)
+                        got[on] += op["sign"] * partner[on]
+            assert np.abs(got - want).max() < 1e-12   # (terms are added in another order)
+
+
 def measure_partial_model(psi_local, n, nl, rank, world, peers, positions):
     """What qca_exact_measure_partial returns, restated in numpy (rotation drops out of |.|^2, |w|)."""
     sums = np.zeros(4 * n)

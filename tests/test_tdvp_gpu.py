@@ -257,8 +257,11 @@ def test_native_krylov_exponential_matches_dense(chi, m, t):
     assert (h - h.conj().T).abs().max().item() < 1e-10 * h.abs().max().item()
     lam, vec = torch.linalg.eigh(0.5 * (h + h.conj().T))
     want = (vec * torch.exp(-1j * t * lam)) @ (vec.conj().T @ theta.reshape(-1))
-    got = heff_expm(left, right, algo._site_operator("two", i), theta, min(m, dim), t).reshape(-1)
+    got = heff_expm(left, right, algo._site_operator("two", i), theta, min(m, dim), t).reshape(-1)   # Jacobi
     assert (got - want).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item())
+    for bound in (algo._bound, 3.0 * algo._bound, 1e-3):   # Chebyshev (tight, loose), bound too small -> Jacobi
+        got = heff_expm(left, right, algo._site_operator("two", i), theta, min(m, dim), t, spectral_bound=bound).reshape(-1)
+        assert (got - want).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item()), bound
     # one-site tensor, backwards in time (tdvp.py:120-127)
     left1, right1 = algo._env_left(i - 1), algo._env_right(i + 1)
     psi = algo._A[i]
@@ -267,5 +270,5 @@ def test_native_krylov_exponential_matches_dense(chi, m, t):
     h = torch.stack([algo._apply_one_site(left1, right1, algo._W[i], eye[k]).reshape(-1) for k in range(dim)], dim=1)
     lam, vec = torch.linalg.eigh(0.5 * (h + h.conj().T))
     want = (vec * torch.exp(1j * t * lam)) @ (vec.conj().T @ psi.reshape(-1))
-    got = heff_expm(left1, right1, algo._site_operator("one", i), psi, min(m, dim), -t).reshape(-1)
+    got = heff_expm(left1, right1, algo._site_operator("one", i), psi, min(m, dim), -t, spectral_bound=algo._bound).reshape(-1)
     assert (got - want).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item())
