@@ -216,11 +216,16 @@ def b200_arm(args) -> None:
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ncu_range = os.environ.get("QCA_NCU_RANGE") == "1"   # ncu --profile-from-start off: only the timed region
+    if ncu_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         one_step(eng)
     ev1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     st = eng.stats()

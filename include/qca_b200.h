@@ -101,6 +101,8 @@ int32_t qca_plan_remote(const qca_rule_t* rule, int32_t world_size, int32_t rank
  * Every launch has `nslots` remote operand slots; slot s of pass p carries, for the amplitudes x whose
  * rotation is r, term op_of[p][s][r] of the qca_plan_remote list (-1: none), with
  *   r(x) = (rot_word >> 2 * ((x_local >> rot_shift) & 15)) & 3  <  npasses.
+ * nslots == 0: the terms do not fit two slots per pass (three terms on a single-pass register): such
+ * registers run on the generic kernel.
  * Each term is applied in exactly one pass for every x, and every pass pulls (nearly) the same share of
  * every term over NVLink, so the NVLink time overlaps the HBM time of every launch.  (The `pass` field of
  * qca_remote_op_t is the static placement the generic kernel uses instead.) */
@@ -269,6 +271,12 @@ int32_t qca_exact_ipc_count(qca_exact_t h);
 int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IPC_HANDLE_BYTES]);
 /* handles: [world_size][count][QCA_IPC_HANDLE_BYTES] gathered from all ranks */
 int32_t qca_exact_ipc_import(qca_exact_t h, const uint8_t* handles, int32_t world_size, int32_t count);
+
+/* Profiling aid (one GPU): a sharded engine whose "partner" vectors are its own planes and whose
+ * cross-rank barrier is a no-op.  The launches, kernels and byte counts are those of rank `rank` of a
+ * world_size job (remote operands come from local HBM instead of NVLink); the numbers it computes are
+ * meaningless.  Used by scratch/loopback_prof.py to profile the sharded tile-pass kernel under ncu. */
+int32_t qca_exact_loopback_peers(qca_exact_t h);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,7 @@ SYMBOLS = {
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),
     "qca_exact_ipc_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qca_exact_ipc_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "qca_exact_loopback_peers": (C.c_int32, [C.c_void_p]),
 }
 
 
@@ -250,6 +251,10 @@ class ExactEngine:
         """table: uint8[world, count, 64] gathered from all ranks."""
         table = np.ascontiguousarray(table, dtype=np.uint8)
         check(lib.qca_exact_ipc_import(self._h, C.c_void_p(table.ctypes.data), table.shape[0], table.shape[1]))
+
+    def loopback_peers(self) -> None:
+        """Profiling aid: see qca_exact_loopback_peers."""
+        check(lib.qca_exact_loopback_peers(self._h))
 
     def plane_flags(self) -> tuple[bool, bool]:
         re, im = C.c_int32(), C.c_int32()

@@ -252,6 +252,7 @@ struct Engine {
     double* peer_plane[kMaxWorld][3][2] = {};
     unsigned long long* peer_flags[kMaxWorld] = {};
     bool peers_ready = false;
+    bool loopback = false;   // profiling aid: "partners" are this rank's own planes, no cross-rank barrier
     unsigned long long epoch = 0;
     // stats
     qca_exact_stats_t st{};
@@ -327,6 +328,7 @@ static int32_t build_tables(Engine* e) {
     e->fast_path = (e->local_bits >= kTile) && d <= 4 && (e->world == 1 || e->passes.size() >= 2);
     for (int j = 0; j < e->shard.nins; ++j) e->fast_path = e->fast_path && e->shard.pos[j] >= kTile;
     for (const qca_remote_op_t& op : e->remote) e->fast_path = e->fast_path && op.mask != 0;
+    if (!e->remote.empty() && e->rotation.nslots == 0) e->fast_path = false;   // more terms than the fast kernel has slots
     e->d_tab_lo.assign(e->passes.size(), nullptr);
     e->d_tab_hi.assign(e->passes.size(), nullptr);
     e->win_shift.assign(e->passes.size(), 0);
@@ -348,7 +350,7 @@ static int32_t build_tables(Engine* e) {
 }
 
 static int32_t launch_barrier(Engine* e) {
-    if (e->world == 1) return QCA_OK;
+    if (e->world == 1 || e->loopback) return QCA_OK;
     QCA_REQUIRE(e->peers_ready, QCA_ERR_STATE, "sharded engine used before qca_exact_ipc_import");
     BarrierArgs b{};
     for (int r = 0; r < e->world; ++r) b.flags[r] = e->peer_flags[r];
@@ -372,6 +374,15 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     a.tab_hi = e->d_tab_hi[pass_index];
     const int T = ps.low_bits + ps.high_bits;
     a.ntiles = e->namps >> T;
+    if (T == kTile) {   // fast kernel: index bits of register row r (tile bits 9..12), expanded to global positions
+        ShardMap bits_only = e->shard;
+        bits_only.rank_or = 0;
+        for (unsigned r = 0; r < 16; ++r) {
+            const unsigned long long y = (unsigned long long)r << kRowShift;
+            const unsigned long long off = (y & ((1ull << ps.low_bits) - 1ull)) | ((y >> ps.low_bits) << ps.high_start);
+            a.row_xg[r] = expand_index(off, bits_only);
+        }
+    }
     int smem = (int)(sizeof(double) << T);
     const bool wide = (e->rule.ncells > 31);
     PassKernel kern = nullptr;
@@ -1112,6 +1123,20 @@ int32_t qca_exact_ipc_export(qca_exact_t h, int32_t index, uint8_t handle[QCA_IP
     cudaIpcMemHandle_t mh;
     QCA_CUDA(cudaIpcGetMemHandle(&mh, ipc_buffer(e, index)));
     memcpy(handle, &mh, sizeof(mh));
+    return QCA_OK;
+}
+
+int32_t qca_exact_loopback_peers(qca_exact_t h) {
+    QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
+    Engine* e = &h->e;
+    QCA_REQUIRE(e->world > 1 && !e->peers_ready, QCA_ERR_STATE, "loopback needs a sharded engine without imported peers");
+    for (int r = 0; r < e->world; ++r) {
+        for (int v = 0; v < 3; ++v)
+            for (int p = 0; p < 2; ++p) e->peer_plane[r][v][p] = e->plane[v][p];
+        e->peer_flags[r] = e->d_flags;
+    }
+    e->loopback = true;
+    e->peers_ready = true;
     return QCA_OK;
 }
 

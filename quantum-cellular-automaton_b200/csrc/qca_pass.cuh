@@ -62,6 +62,7 @@ struct PassArgs {
     double gamma;
     EpiStream s[kMaxStreams];
     int nstreams;
+    unsigned long long row_xg[16];    // fast kernel: GLOBAL index bits of register row e (sharded qubits inserted, no rank bits)
     RemoteSlot rs[kMaxRemoteSlots];   // fast kernel only
     int nrem;
     unsigned rot_word;     // r(x) = (rot_word >> 2 * ((x_local >> rot_shift) & 15)) & 3
@@ -177,8 +178,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    if (mbar_try_wait(bar, parity)) return;
+static __device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 40000000000ll) {  // ~20 s: a partner's memory never answered; fail instead of hanging
@@ -186,6 +186,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -200,11 +203,16 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 //     pairs of a warp's row are 512 contiguous bytes (128-byte pieces when the tile keeps fewer than 6
 //     low bits) -- each row completing on its own mbarrier.  The two mechanisms are independent: a
 //     slow NVLink row never holds back the HBM rows behind it (with cp.async groups, which retire in
-//     order, it did), and the remote ring runs a full DC rows ahead.
-constexpr int kRingRowsTotal = 12;
+//     order, it did), and the remote ring runs a full DC rows ahead.  Which rows a slot is active on
+//     (and for which term) is decided once per tile in a compact loop, two words per thread: the
+//     per-row cost of an idle slot is one predicate (the first version re-derived everything per
+//     row and tripled the instruction count of the launch: ncu, profiles/r01_pass_v4_*).
+constexpr int kRingRowsTotal = 12;   // 64 KiB tile + 48 KiB ring = 112 KiB: two CTAs per SM, not a byte to spare
 constexpr int kPassWarps = kPassThreads / 32;
 constexpr int kPassMbarBytes = kPassWarps * 8 * 8;  // up to 8 mbarriers per warp (slots x rows)
-constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16 + kPassMbarBytes;  // 112.5 KiB: 2 CTAs/SM
+constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16;
+// with remote slots the last ring row is given up for the mbarriers (occupancy would halve otherwise)
+__host__ __device__ constexpr int ring_rows(int nrem) { return nrem == 0 ? kRingRowsTotal : kRingRowsTotal - 1; }
 
 // ring depth (rows of look-ahead) of a remote / a local operand.  HBM needs the deeper ring (measured:
 // a 4-row local ring costs 25 % of the pass bandwidth); the remote ring covers the NVLink latency with
@@ -213,7 +221,7 @@ __host__ __device__ constexpr int ring_rem(int nrem, int rd) {
     return nrem == 0 ? 0 : (nrem == 1 ? rd : 4);
 }
 __host__ __device__ constexpr int ring_unc(int nunc, int nrem, int rd) {
-    return nunc == 0 ? 0 : (kRingRowsTotal - nrem * ring_rem(nrem, rd)) / nunc;
+    return nunc == 0 ? 0 : (ring_rows(nrem) - nrem * ring_rem(nrem, rd)) / nunc;
 }
 
 // L: contiguous low bits of the tile, M = 13 - L strided bits at H0.
@@ -226,8 +234,9 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     constexpr int DU = ring_unc(NUNC, NREM, RD), DC = ring_rem(NREM, RD);   // look-ahead per operand kind
     constexpr int CHUNK_LANES = (L >= 6) ? 32 : (1 << (L - 1));  // lanes whose pairs are contiguous in global memory
     constexpr int ISSUERS = 32 / CHUNK_LANES;                    // bulk copies per warp and row
-    static_assert(NUNC * DU + NREM * DC <= kRingRowsTotal, "ring budget");
-    static_assert(NREM * DC <= 8, "mbarrier budget");
+    static_assert(NUNC * DU + NREM * DC <= ring_rows(NREM), "ring budget");
+    static_assert(NUNC == 0 || DU >= 1, "local ring");
+    static_assert((32 / ((L >= 6) ? 32 : (1 << (L - 1)))) * NREM * DC <= 32, "mbarrier budget: 32 per warp");
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
     static_assert(NUNC >= 0 && NUNC <= 2 && NREM >= 0 && NREM <= kMaxRemoteSlots, "operands");
     static_assert(L >= 4, "rows of at least 128 bytes");
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     double2* tile2 = reinterpret_cast<double2*>(tile);
     double2* ring = tile2 + (1 << (kTile - 1));            // local operand k: rows [k*DU, (k+1)*DU)
     double2* rring = ring + NUNC * DU * kPassThreads;      // remote slot k: rows [k*DC, (k+1)*DC)
-    const unsigned mbar0 = smem_u32(ring + kRingRowsTotal * kPassThreads) + warp * 64u;   // this warp's mbarriers
+    const unsigned mbar0 = smem_u32(ring + (kRingRowsTotal - 1) * kPassThreads) + warp * 256u;  // this warp's mbarriers (last ring row)
     auto row_x = [&](int e) -> I {  // index of the pair (row e, this thread); folds to x_thr | const << H0
         const unsigned ye = (unsigned)e << kRowShift;
         return x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
@@ -264,30 +273,52 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     auto remote_slot = [&](int k, int e) -> double2* {
         return rring + ((k * DC + (e % DC)) * kPassThreads + tid);
     };
-    auto remote_bar = [&](int k, int e) -> unsigned { return mbar0 + (unsigned)(k * DC + (e % DC)) * 8u; };
-    // the term slot k carries at x (rotation), and whether it is active there
-    auto remote_alt = [&](int k, I x, bool* on) -> const RemoteAlt* {
-        const unsigned rot = (a.rot_word >> (2u * ((unsigned)(x >> a.rot_shift) & 15u))) & 3u;
-        const RemoteAlt* al = &a.rs[k].alt[rot];
-        *on = (al->mask >> ((unsigned)(x >> al->shift) & 15u)) & 1u;
-        return al;
+    constexpr int NBAR = NREM * DC;                      // mbarriers per piece
+    const unsigned piece = lane / CHUNK_LANES;           // which contiguous piece of the warp's row this lane reads
+    auto remote_bar = [&](int k, int e) -> unsigned { return mbar0 + (piece * NBAR + (unsigned)(k * DC + (e % DC))) * 8u; };
+    // Per tile: on which of its 16 rows each slot is active for this thread (act[k], bit e) and with which
+    // rotation (rot0/rot1: low/high bit per row).  Both read index bits >= 13 only, so they are constant over
+    // a piece: the lanes of a piece evaluate one row each (two for 8-lane pieces) and share the answers
+    // through warp votes -- ~25 instructions per tile instead of ~20 per row.
+    unsigned act[NREM ? NREM : 1] = {0};
+    unsigned rot0 = 0, rot1 = 0;
+    if (NREM) {
+        constexpr int ROWS_PER_LANE = (CHUNK_LANES >= 16) ? 1 : 16 / CHUNK_LANES;
+        constexpr int FIELD = (CHUNK_LANES >= 16) ? 16 : CHUNK_LANES;      // rows answered by one vote
+        const unsigned field_shift = (CHUNK_LANES >= 32) ? 0u : piece * CHUNK_LANES;
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_LANE; ++q) {
+            const unsigned e = ((lane & (CHUNK_LANES - 1)) + q * CHUNK_LANES) & 15u;
+            const unsigned ye = e << kRowShift;
+            const I x = x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
+            const unsigned rot = (a.rot_word >> (2u * ((unsigned)(x >> a.rot_shift) & 15u))) & 3u;
+            const unsigned v0 = __ballot_sync(0xffffffffu, rot & 1u), v1 = __ballot_sync(0xffffffffu, rot & 2u);
+            rot0 |= ((v0 >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+            rot1 |= ((v1 >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+#pragma unroll
+            for (int k = 0; k < NREM; ++k) {
+                const RemoteAlt* al = &a.rs[k].alt[rot];
+                const unsigned vk = __ballot_sync(0xffffffffu, (al->mask >> ((unsigned)(x >> al->shift) & 15u)) & 1u);
+                act[k] |= ((vk >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+            }
+        }
+    }
+    auto row_rot = [&](int e) -> unsigned { return ((rot0 >> e) & 1u) | (((rot1 >> e) & 1u) << 1); };
+    // earlier ACTIVE uses of the ring slot of row e decide the phase of its mbarrier (idle rows never arrive)
+    auto uses_before = [](int e) -> unsigned {   // bits e' < e with e' == e (mod DC); folds to a constant
+        unsigned m = 0;
+        for (int q = e % (DC ? DC : 1); q < e; q += (DC ? DC : 1)) m |= 1u << q;
+        return m;
     };
-    // row e of every remote slot: the first lane of each contiguous piece issues its bulk copy (or just
-    // arrives when the term is inactive there: activity is constant over a piece)
+    // row e of every remote slot: the first lane of each contiguous piece issues its bulk copy
     auto remote_issue = [&](int e) {
 #pragma unroll
         for (int k = 0; k < NREM; ++k) {
-            const I x = row_x(e);
-            bool on;
-            const RemoteAlt* al = remote_alt(k, x, &on);
-            if ((lane & (CHUNK_LANES - 1)) == 0) {
+            if (((act[k] >> e) & 1u) && (lane & (CHUNK_LANES - 1)) == 0) {
+                const RemoteAlt* al = &a.rs[k].alt[row_rot(e)];
                 const unsigned bar = remote_bar(k, e);
-                if (on) {
-                    mbar_arrive_expect_tx(bar, CHUNK_LANES * 16);
-                    bulk_g2s(smem_u32(remote_slot(k, e)), al->ptr[plane] + x, CHUNK_LANES * 16, bar);
-                } else {
-                    mbar_arrive(bar);
-                }
+                mbar_arrive_expect_tx(bar, CHUNK_LANES * 16);
+                bulk_g2s(smem_u32(remote_slot(k, e)), al->ptr[plane] + row_x(e), CHUNK_LANES * 16, bar);
             }
         }
     };
@@ -297,12 +328,9 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     };
     // ---- start streaming the epilogue operands: the far ones first ---------------------------------
     if (NREM) {
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < NREM * DC; ++i) mbar_init(mbar0 + i * 8u, ISSUERS);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
+        if (lane < ISSUERS * NBAR) mbar_init(mbar0 + lane * 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < DC; ++e) remote_issue(e);
@@ -335,6 +363,9 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
 #pragma unroll
     for (int b = 0; b < 8; ++b) sgn[b] = ((tid >> b) & 1u) ? -1.0 : 1.0;
 
+    // global index of this thread's pairs without the row bits (sharded qubits of this rank inserted)
+    const unsigned long long xg_thr = expand_index((unsigned long long)x_thr, a.shard);
+
     __syncthreads();
 
 #pragma unroll
@@ -342,7 +373,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
         unsigned la0, la1;
         // windows are cut out of the GLOBAL index (sharded qubits of this rank inserted); every
         // sharded position is >= 13, so local bits 0..12 are global bits 0..12
-        const unsigned long long xg = expand_index((unsigned long long)row_x(e), a.shard);
+        const unsigned long long xg = xg_thr | a.row_xg[e];
         if (FLIP_LOW) {
             const int S = 9 - d;
             const unsigned w = (unsigned)(xg >> (9 - 2 * d)) & ((1u << (4 + 3 * d)) - 1u);
@@ -395,16 +426,14 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
             }
         }
         if (NREM) {
-            const I x = row_x(e);
 #pragma unroll
             for (int k = 0; k < NREM; ++k) {
-                bool on;
-                const RemoteAlt* al = remote_alt(k, x, &on);
-                if (on) {
-                    mbar_wait(remote_bar(k, e), (unsigned)(e / DC) & 1u);
+                if ((act[k] >> e) & 1u) {
+                    mbar_wait(remote_bar(k, e), __popc(act[k] & uses_before(e)) & 1u);
                     const double2 sv = *remote_slot(k, e);
-                    r.x = fma(al->coef, sv.x, r.x);
-                    r.y = fma(al->coef, sv.y, r.y);
+                    const double coef = a.rs[k].alt[row_rot(e)].coef;
+                    r.x = fma(coef, sv.x, r.x);
+                    r.y = fma(coef, sv.y, r.y);
                 }
             }
         }

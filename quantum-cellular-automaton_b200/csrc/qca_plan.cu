@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 
 #include "qca_common.cuh"
@@ -234,9 +235,15 @@ int32_t plan_rotation(const qca_rule_t& r, int world, int rank, qca_remote_rotat
     out->rot_shift = kTileBits;
     for (unsigned v = 0; v < 16; ++v) out->rot_word |= (v % (unsigned)np) << (2 * v);
     out->nslots = ((int)ops.size() + np - 1) / np;
-    QCA_REQUIRE(out->nslots <= 2, QCA_ERR_UNSUPPORTED, "%zu remote terms over %d passes", ops.size(), np);
+    if (out->nslots > 2) {   // single-pass registers (< 13 local qubits) with three terms: generic kernel only
+        out->nslots = 0;
+        return QCA_OK;
+    }
+    // QCA_FORCE_SLOTS2 (test aid): run the two-slot kernels even when one slot would do
+    const bool force2 = getenv("QCA_FORCE_SLOTS2") != nullptr && !ops.empty() && out->nslots == 1;
+    if (force2) out->nslots = 2;
     for (int j = 0; j < (int)ops.size(); ++j)
-        for (int rot = 0; rot < np; ++rot) out->op_of[(j + rot) % np][j / np][rot] = j;
+        for (int rot = 0; rot < np; ++rot) out->op_of[(j + rot) % np][force2 ? 1 : j / np][rot] = j;
     return QCA_OK;
 }
 
