@@ -232,7 +232,7 @@ struct Engine {
     std::vector<qca_pass_t> passes;
     std::vector<qca_remote_op_t> remote;
     qca_remote_rotation_t rotation{};  // fast kernel: how the remote terms rotate over the passes
-    int remote_rows = 4;               // rows of the remote operand ring (QCA_REMOTE_RING=6: deeper, shallower local ring)
+    int remote_rows = 6;               // rows of the remote operand ring (QCA_REMOTE_RING=4: shallower, deeper local ring)
     double remote_fraction[64] = {};   // per sharded qubit (global bit): fraction of the plane its term reads
     double2* staging = nullptr;
     unsigned long long staging_amps = 0;
@@ -853,7 +853,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     qca::plan_passes(e->local_bits, e->passes);
     if (int32_t rc = qca::plan_remote(*rule, world_size, rank, e->remote)) { delete h; return rc; }
     if (int32_t rc = qca::plan_rotation(*rule, world_size, rank, &e->rotation)) { delete h; return rc; }
-    if (const char* env = getenv("QCA_REMOTE_RING")) e->remote_rows = (atoi(env) == 6) ? 6 : 4;
+    if (const char* env = getenv("QCA_REMOTE_RING")) e->remote_rows = (atoi(env) == 4) ? 4 : 6;
     for (const qca_remote_op_t& op : e->remote)  // fraction of the plane the term reads on this rank
         e->remote_fraction[op.qubit] = op.window_bits <= 4
             ? (double)__builtin_popcount(op.mask & 0xffffu) / 16.0 : 1.0;   // the mask is replicated over 16 entries

@@ -214,9 +214,9 @@ constexpr int kPassSmemBytes = (8 << kTile) + kRingRowsTotal * kPassThreads * 16
 // with remote slots the last ring row is given up for the mbarriers (occupancy would halve otherwise)
 __host__ __device__ constexpr int ring_rows(int nrem) { return nrem == 0 ? kRingRowsTotal : kRingRowsTotal - 1; }
 
-// ring depth (rows of look-ahead) of a remote / a local operand.  HBM needs the deeper ring (measured:
-// a 4-row local ring costs 25 % of the pass bandwidth); the remote ring covers the NVLink latency with
-// RD rows (4, or 6 with one slot: QCA_REMOTE_RING=6) because its rows complete independently.
+// ring depth (rows of look-ahead) of a remote / a local operand: one remote slot gets RD rows (6 by
+// default: 4.40 against 4.32 steps/s with RD = 4 at N = 30 on 8 GPUs; QCA_REMOTE_RING=4 selects the
+// latter), two slots 4 rows each; the local operands share the rest.
 __host__ __device__ constexpr int ring_rem(int nrem, int rd) {
     return nrem == 0 ? 0 : (nrem == 1 ? rd : 4);
 }
