@@ -99,3 +99,112 @@ def clenshaw_exp(kmat: np.ndarray, phi: np.ndarray, a: np.ndarray, bound: float,
     for k in range(K - 1, 0, -1):
         b1, b2 = a[k] * phi + sign * (2.0 / bound) * (kmat @ b1) + b2, b1
     return a[0] * phi + sign * (1.0 / bound) * (kmat @ b1) + b2
+
+
+# ---------------------------------------------------------------------------------------------
+# Model of the REMOTE OPERAND SLOTS of the fast tile-pass kernel (csrc/qca_pass.cuh, NREM > 0):
+# per-tile activity decided by warp votes, one bulk copy per contiguous piece into a ring slot, one
+# mbarrier per (piece, slot, ring row) whose phase is the parity of its ACTIVE earlier uses.
+# Follows the kernel statement by statement; the CPU tests use it to prove the bookkeeping (which row
+# sits in which ring slot when it is read, which parity is waited for) for every tile geometry.
+# ---------------------------------------------------------------------------------------------
+ROW_SHIFT = 9      # register rows are tile bits 9..12
+ROWS = 16
+
+
+def ring_rows_remote(nrem: int, rd: int) -> int:
+    """ring_rem() of the kernel."""
+    return 0 if nrem == 0 else (rd if nrem == 1 else 4)
+
+
+def remote_slot_trace(ps: dict, tile: int, ops: list, rot: dict, pass_index: int, rd: int = 6):
+    """For one CTA (tile of pass `ps`): returns, for every slot k, a dict (tid, row) -> index of the
+    remote term applied to that thread's pair on that row (as the kernel would), after checking the ring
+    and mbarrier bookkeeping of every warp.  ops / rot: qca_plan_remote / qca_plan_rotation."""
+    L, H0 = ps["low_bits"], ps["high_start"]
+    low_mask = (1 << L) - 1
+    gap = H0 - L
+    t_lo, t_hi = tile & ((1 << gap) - 1), tile >> gap
+    M = 13 - L
+    base = (t_lo << L) | (t_hi << (H0 + M))
+    nrem = rot["nslots"]
+    dc = ring_rows_remote(nrem, rd)
+    chunk_lanes = 32 if L >= 6 else 1 << (L - 1)
+    issuers = 32 // chunk_lanes
+    assert issuers * nrem * dc <= 32                      # mbarrier budget of a warp
+
+    def row_x(x_thr, e):
+        ye = e << ROW_SHIFT
+        return x_thr | (ye & low_mask) | ((ye >> L) << H0)
+
+    def alt(k, r):                                        # a.rs[k].alt[r]
+        j = int(rot["op_of"][pass_index, k, r]) if r < rot["npasses"] else -1
+        return (j, ops[j]["mask"], ops[j]["shift"]) if j >= 0 else (-1, 0, 0)
+
+    applied = [dict() for _ in range(nrem)]
+    for warp in range(8):
+        x_thr = [base | ((tid << 1) & low_mask) | (((tid << 1) >> L) << H0) for tid in range(32 * warp, 32 * warp + 32)]
+        # --- per-tile decisions through votes -------------------------------------------------
+        rows_per_lane = 1 if chunk_lanes >= 16 else 16 // chunk_lanes
+        field = 16 if chunk_lanes >= 16 else chunk_lanes
+        act = [[0] * 32 for _ in range(nrem)]
+        rot0, rot1 = [0] * 32, [0] * 32
+        for q in range(rows_per_lane):
+            e_of = [((lane & (chunk_lanes - 1)) + q * chunk_lanes) & 15 for lane in range(32)]
+            x_of = [row_x(x_thr[lane], e_of[lane]) for lane in range(32)]
+            r_of = [(rot["rot_word"] >> (2 * ((x_of[lane] >> rot["rot_shift"]) & 15))) & 3 for lane in range(32)]
+            v0 = sum(((r_of[lane] & 1) != 0) << lane for lane in range(32))
+            v1 = sum(((r_of[lane] & 2) != 0) << lane for lane in range(32))
+            vk = []
+            for k in range(nrem):
+                bits = 0
+                for lane in range(32):
+                    _, mask, shift = alt(k, r_of[lane])
+                    bits |= ((mask >> ((x_of[lane] >> shift) & 15)) & 1) << lane
+                vk.append(bits)
+            for lane in range(32):
+                fs = 0 if chunk_lanes >= 32 else (lane // chunk_lanes) * chunk_lanes
+                rot0[lane] |= ((v0 >> fs) & ((1 << field) - 1)) << (q * field)
+                rot1[lane] |= ((v1 >> fs) & ((1 << field) - 1)) << (q * field)
+                for k in range(nrem):
+                    act[k][lane] |= ((vk[k] >> fs) & ((1 << field) - 1)) << (q * field)
+        # the votes must agree with what every lane would find for ITS OWN pair on every row
+        for lane in range(32):
+            for e in range(ROWS):
+                x = row_x(x_thr[lane], e)
+                r = (rot["rot_word"] >> (2 * ((x >> rot["rot_shift"]) & 15))) & 3
+                assert r == ((rot0[lane] >> e) & 1) | (((rot1[lane] >> e) & 1) << 1)
+                for k in range(nrem):
+                    _, mask, shift = alt(k, r)
+                    assert ((mask >> ((x >> shift) & 15)) & 1) == (act[k][lane] >> e) & 1
+        # --- ring and mbarrier bookkeeping, piece by piece -------------------------------------
+        for piece in range(issuers):
+            lead = piece * chunk_lanes                      # issuing lane
+            for k in range(nrem):
+                a_bits = act[k][lead]
+                assert all(act[k][lane] == a_bits for lane in range(lead, lead + chunk_lanes))   # constant over a piece
+                slot_row = [None] * dc                      # which row's data a ring slot holds
+                completed = [0] * dc                        # completed phases of the slot's mbarrier
+                def issue(e):
+                    if (a_bits >> e) & 1:
+                        assert slot_row[e % dc] is None     # the previous occupant has been consumed
+                        slot_row[e % dc] = e
+                        completed[e % dc] += 1              # arrive.expect_tx + complete_tx: the phase completes
+                for e in range(dc):
+                    issue(e)
+                for e in range(ROWS):
+                    if (a_bits >> e) & 1:
+                        uses_before = sum(1 << q for q in range(e % dc, e, dc))
+                        parity = bin(a_bits & uses_before).count("1") & 1
+                        # try_wait.parity(p) succeeds once the phase with that parity has completed:
+                        # phases 0..completed-1 are done, the waited one is number (completed - 1)
+                        assert completed[e % dc] >= 1 and (completed[e % dc] - 1) & 1 == parity
+                        assert slot_row[e % dc] == e
+                        slot_row[e % dc] = None
+                        for lane in range(lead, lead + chunk_lanes):
+                            r = ((rot0[lane] >> e) & 1) | (((rot1[lane] >> e) & 1) << 1)
+                            applied[k][(32 * warp + lane, e)] = alt(k, r)[0]
+                    if e + dc < ROWS:
+                        issue(e + dc)
+                assert all(s is None for s in slot_row)
+    return applied

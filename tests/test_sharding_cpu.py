@@ -206,3 +206,45 @@ def test_sharded_engine_refuses_without_device():
     with pytest.raises(qca_b200.QcaError) as e:
         _lib.plan_remote(qca_b200.Rules(12, range(1, 2), 1), 3, 0)
     assert e.value.code == _lib.QCA_ERR_ARG
+
+
+@pytest.mark.parametrize("world,n,d,lo,hi", [(2, 18, 2, 2, 4), (2, 20, 1, 1, 2), (4, 19, 2, 2, 4), (4, 22, 1, 1, 2),
+                                             (8, 18, 1, 1, 2), (8, 20, 2, 2, 4), (8, 22, 1, 1, 2), (8, 26, 2, 2, 4)])
+@pytest.mark.parametrize("rd", [4, 6])
+def test_fast_kernel_remote_slot_bookkeeping(world, n, d, lo, hi, rd):
+    """Statement-by-statement model of the remote operand slots of the fast tile-pass kernel
+    (pass_model.remote_slot_trace): warp votes reproduce every lane's own decision, activity is constant
+    over a bulk-copy piece, every ring slot holds the row that is read from it, every mbarrier wait uses
+    the parity of the phase that row completed, and over the passes every amplitude receives every
+    remote term exactly where the plan says."""
+    rules = RuleNS(n, d, lo, hi)
+    rbits = world.bit_length() - 1
+    nl = n - rbits
+    passes = _lib.plan_passes(nl)
+    assert nl >= 13 and len(passes) >= 2
+    rng = np.random.default_rng(n + world)
+    for rank in sorted(set([0, world - 1, int(rng.integers(world))])):
+        ops = _lib.plan_remote(rules, world, rank)
+        rot = _lib.plan_rotation(rules, world, rank)
+        if not ops or rot["nslots"] == 0:
+            continue
+        counts = {}
+        for p, ps in enumerate(passes):
+            ntiles = 1 << (nl - 13)
+            tiles = sorted(set([0, ntiles - 1] + [int(t) for t in rng.integers(ntiles, size=3)]))
+            for tile in tiles:
+                applied = pass_model.remote_slot_trace(ps, tile, ops, rot, p, rd)
+                L, H0 = ps["low_bits"], ps["high_start"]
+                for k, table in enumerate(applied):
+                    for (tid, e), j in table.items():
+                        assert j >= 0
+                        gap = H0 - L
+                        base = ((tile & ((1 << gap) - 1)) << L) | ((tile >> gap) << (H0 + 13 - L))
+                        y = (tid << 1) | (e << 9)
+                        x = base | (y & ((1 << L) - 1)) | ((y >> L) << H0)
+                        op = ops[j]
+                        assert (op["mask"] >> ((x >> op["shift"]) & 15)) & 1          # the term is active at x
+                        r = (rot["rot_word"] >> (2 * ((x >> rot["rot_shift"]) & 15))) & 3
+                        assert rot["op_of"][p, k, r] == j                              # and this pass/slot carries it
+                        counts[(x, j)] = counts.get((x, j), 0) + 1
+        assert all(c == 1 for c in counts.values())
