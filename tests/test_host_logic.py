@@ -144,3 +144,71 @@ def test_clenshaw_in_rotated_frame_equals_calculate_U(n, d, lo, hi, tau):
     phi = psi / rot
     out = rot * pass_model.clenshaw_exp(kmat, phi, a, bound, np.sign(tau))
     assert np.abs(out - u @ psi).max() < 1e-13
+
+
+def test_site_operator_csr_equals_the_einsum_contraction():
+    """linalg.site_operator_csr (the sparse channel mix between the two DMMA contractions of H_eff) against
+    the reference's dense contraction of the MPO tensors (tdvp.py:280-283, 350-365), plus its masks of
+    structurally empty channels."""
+    from qca_b200.linalg import site_operator_csr
+    rng = np.random.default_rng(0)
+    for (n, d, lo, hi) in [(8, 1, 1, 2), (9, 2, 2, 4), (10, 3, 2, 5)]:
+        w = qca_b200.MPO.hamiltonian_from_rules(qca_b200.Rules(n, range(lo, hi), d)).W
+        w1, w2 = np.asarray(w[n // 2 - 1]), np.asarray(w[n // 2])
+        wl, wr = w1.shape[2], w2.shape[3]
+        # two sites
+        rowptr, col, val, (g, a, b) = site_operator_csr(w1, w2)
+        assert (g, a, b) == (4, wl, wr) and rowptr.shape == (4 * wr + 1,)
+        dense = np.zeros((4 * wr, 4 * wl), dtype=complex)
+        for r in range(4 * wr):
+            dense[r, col[rowptr[r]:rowptr[r + 1]]] = val[rowptr[r]:rowptr[r + 1]]
+        t1 = rng.standard_normal((2, 2, wl, 3, 5)) + 1j * rng.standard_normal((2, 2, wl, 3, 5))
+        want = np.einsum("cdmn,bcmyu->bdnyu", w2, np.einsum("abwm,acwyu->bcmyu", w1, t1))
+        got = (dense @ t1.reshape(4 * wl, -1)).reshape(2, 2, wr, 3, 5)
+        assert np.abs(got - want).max() < 1e-13
+        assert int(rowptr[-1]) < dense.size // 4          # the automaton's MPO is very sparse
+        # one site
+        rowptr, col, val, (g, a, b) = site_operator_csr(w1)
+        dense = np.zeros((2 * w1.shape[3], 2 * wl), dtype=complex)
+        for r in range(dense.shape[0]):
+            dense[r, col[rowptr[r]:rowptr[r + 1]]] = val[rowptr[r]:rowptr[r + 1]]
+        t1 = rng.standard_normal((2, wl, 3, 5)) + 1j * rng.standard_normal((2, wl, 3, 5))
+        want = np.einsum("abwm,awyu->bmyu", w1, t1)
+        assert np.abs((dense @ t1.reshape(2 * wl, -1)).reshape(want.shape) - want).max() < 1e-13
+    # bond matrix: identity over the MPO channels
+    rowptr, col, val, (g, a, b) = site_operator_csr(None, 6)
+    assert g == 1 and list(col) == list(range(6)) and np.all(val == 1)
+
+
+def test_heff_workspace_is_sized_on_the_host():
+    """qca_heff_workspace_bytes is pure host logic: grows with the Krylov dimension and rejects bad shapes."""
+    import ctypes as C
+    h = _lib.HeffStruct(1, 1, 1, 1, 1, 64, 48, 6, 6, 4, 1, (C.c_uint32 * 4)(0x17, 0x2b, 0x17, 0x2b), (C.c_uint32 * 4)(0x35, 0x35, 0x1b, 0x1b))
+    sizes = []
+    for m in (0, 1, 8, 64):
+        n = C.c_uint64()
+        _lib.check(_lib.lib.qca_heff_workspace_bytes(C.byref(h), m, C.byref(n)))
+        sizes.append(n.value)
+    dim = 4 * 64 * 48 * 16
+    assert sizes[0] < sizes[2] < sizes[3] and sizes[3] - sizes[2] == 56 * dim
+    n = C.c_uint64()
+    assert _lib.lib.qca_heff_workspace_bytes(C.byref(h), 65, C.byref(n)) == _lib.QCA_ERR_ARG
+    h.g = 3
+    assert _lib.lib.qca_heff_workspace_bytes(C.byref(h), 4, C.byref(n)) == _lib.QCA_ERR_ARG
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the oracle's restatement of the reference's dense algorithm on host cores)."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-num-cells", "8"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
