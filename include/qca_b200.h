@@ -123,6 +123,10 @@ typedef struct qca_exact* qca_exact_t;
 #define QCA_FLAG_FORCE_COMPLEX 1u /* keep both real planes even if the rotated state is real */
 #define QCA_FLAG_PROFILE 2u       /* record a CUDA-event pair around every kernel launch */
 #define QCA_FLAG_LOOSE_BOUND 4u   /* scale H by the Gershgorin bound only (skip the block-Lanczos bound) */
+#define QCA_FLAG_FUSED_MEASURE 8u   /* measure with one read of the state per tile pass (csrc/qca_measure.cu; single-plane
+                                       states on >= 13 local qubits) instead of one read per cell.  Default on one GPU;
+                                       sharded engines opt in with this flag or the environment variable QCA_FUSED_MEASURE */
+#define QCA_FLAG_PERCELL_MEASURE 16u /* always use the per-cell measurement kernels (also: environment QCA_PERCELL_MEASURE) */
 
 /* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U
  * (dense 2^N x 2^N) the engine keeps only the rule.  world_size/rank shard the

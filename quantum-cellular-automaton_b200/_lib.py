@@ -30,6 +30,8 @@ QCA_OK, QCA_ERR_ARG, QCA_ERR_CUDA, QCA_ERR_NOMEM, QCA_ERR_STATE, QCA_ERR_UNSUPPO
 QCA_FLAG_FORCE_COMPLEX = 1
 QCA_FLAG_PROFILE = 2
 QCA_FLAG_LOOSE_BOUND = 4
+QCA_FLAG_FUSED_MEASURE = 8
+QCA_FLAG_PERCELL_MEASURE = 16
 QCA_IPC_HANDLE_BYTES = 64
 
 

@@ -17,6 +17,7 @@
 #include "qca_common.cuh"
 #include "qca_plan.h"
 #include "qca_pass.cuh"
+#include "qca_measure.h"
 
 namespace qca {
 
@@ -637,7 +638,15 @@ static int32_t measure_partial(Engine* e, double* sums) {
     auto blocks_for = [&](unsigned long long npairs) {
         return (int)std::max<unsigned long long>(1, std::min<unsigned long long>((npairs + kMeasureThreads - 1) / kMeasureThreads, (unsigned long long)e->measure_blocks));
     };
-    for (int bit = 0; bit < e->local_bits; ++bit) {
+    // fused path (csrc/qca_measure.cu): one read of the state per tile pass instead of one per cell
+    const bool fused = (e->flags & QCA_FLAG_FUSED_MEASURE) && e->nplanes == 1 && e->local_bits >= kTile;
+    if (fused) {
+        for (const qca_pass_t& ps : e->passes) {
+            QCA_CHECK(measure_tiles(re, e->namps, ps, e->shard, n, e->d_partials, 2 * e->num_sms, e->d_sums, e->stream));
+            e->st.kernel_launches += 2;
+        }
+    }
+    for (int bit = 0; bit < e->local_bits && !fused; ++bit) {
         const int cell = n - 1 - global_pos(bit, e->shard);
         const unsigned long long npairs = e->namps >> 1;
         const int blocks = blocks_for(npairs);
@@ -848,6 +857,10 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     e->namps = 1ull << e->local_bits;
     qca::plan_shard(*rule, world_size, &e->shard, rank);
     e->flags = flags;
+    // fused measurement: default on one GPU (verified against the per-cell kernels), opt-in when sharded
+    if (getenv("QCA_FUSED_MEASURE") || (world_size == 1 && !getenv("QCA_PERCELL_MEASURE") && !(flags & QCA_FLAG_PERCELL_MEASURE)))
+        e->flags |= QCA_FLAG_FUSED_MEASURE;
+    if (flags & QCA_FLAG_PERCELL_MEASURE) e->flags &= ~QCA_FLAG_FUSED_MEASURE;
     e->num_sms = prop.multiProcessorCount;
     e->bound = qca::spectral_bound(*rule);
     qca::plan_passes(e->local_bits, e->passes);
@@ -869,7 +882,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     }
     e->measure_blocks = e->num_sms * 8;
     bool ok = cudaMalloc(&e->d_maxabs, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&e->d_partials, 4ull * e->measure_blocks * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&e->d_partials, std::max<size_t>(4ull * e->measure_blocks, (size_t)qca::kMeasureTileVals * 2 * e->num_sms) * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_sums, 4ull * rule->ncells * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }

@@ -208,3 +208,53 @@ def remote_slot_trace(ps: dict, tile: int, ops: list, rot: dict, pass_index: int
                         issue(e + dc)
                 assert all(s is None for s in slot_row)
     return applied
+
+
+def measure_tiles_model(vec: np.ndarray, ps: dict):
+    """What csrc/qca_measure.cu computes for one tile pass on a real vector: for every tile bit t that the
+    pass measures, (local index bit, s0, s1, w); follows the kernel's thread/row decomposition."""
+    L, H0, M = ps["low_bits"], ps["high_start"], ps["high_bits"]
+    assert L + M == 13
+    nbits = int(vec.shape[0]).bit_length() - 1
+    first_bit = 0 if M == 0 else L
+    low_mask = (1 << L) - 1
+    tid = np.arange(256, dtype=np.int64)
+    w = np.zeros((13, 256)); s1row = np.zeros((4, 256)); s1b0 = np.zeros(256); tot = np.zeros(256)
+    for tile in range(1 << (nbits - 13)):
+        gap = H0 - L
+        base = ((tile & ((1 << gap) - 1)) << L) | ((tile >> gap) << (H0 + M))
+        y_thr = tid << 1
+        x_thr = base | (y_thr & low_mask) | ((y_thr >> L) << H0)
+        v = np.zeros((16, 256, 2))
+        for e in range(16):
+            ye = e << 9
+            x = x_thr | (ye & low_mask) | ((ye >> L) << H0)
+            v[e, :, 0], v[e, :, 1] = vec[x], vec[x + 1]
+        for e in range(16):
+            nx, ny = v[e, :, 0] ** 2, v[e, :, 1] ** 2
+            tot += nx + ny
+            s1b0 += ny
+            w[0] += v[e, :, 0] * v[e, :, 1]
+            for k in range(4):
+                if (e >> k) & 1:
+                    s1row[k] += nx + ny
+                else:
+                    p = v[e | (1 << k)]
+                    w[9 + k] += v[e, :, 0] * p[:, 0] + v[e, :, 1] * p[:, 1]
+        for b in range(8):
+            if b + 1 >= first_bit:
+                for e in range(16):
+                    p = v[e][tid ^ (1 << b)]
+                    w[b + 1] += v[e, :, 0] * p[:, 0] + v[e, :, 1] * p[:, 1]
+    total = tot.sum()
+    out = []
+    for t in range(first_bit, 13):
+        if t == 0:
+            s1, wt = s1b0.sum(), w[0].sum()
+        elif t <= 8:
+            s1, wt = tot[((tid >> (t - 1)) & 1) == 1].sum(), 0.5 * w[t].sum()
+        else:
+            s1, wt = s1row[t - 9].sum(), w[t].sum()
+        g = t if t < L else H0 + (t - L)
+        out.append((g, total - s1, s1, wt))
+    return out

@@ -239,3 +239,30 @@ def test_tight_bound_large_chain_blocks():
     eng.set_product_state(qca_b200.states.plist("triple_blinker", rules))
     eng.step(1.0, 1)
     assert abs(eng.norm2() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("n,d,lo,hi,state", [(13, 1, 1, 2, "blinker"), (14, 2, 2, 4, "triple_blinker"), (15, 1, 1, 2, "single"),
+                                             (16, 2, 1, 3, "blinker"), (17, 2, 2, 4, "triple_blinker"), (18, 1, 1, 2, "blinker"),
+                                             (21, 2, 2, 4, "triple_blinker"), (25, 1, 1, 2, "triple_blinker")])
+def test_fused_measurement_matches_per_cell_kernels_and_oracle(n, d, lo, hi, state):
+    """csrc/qca_measure.cu (one read of the state per tile pass; the default on one GPU for single-plane
+    states) against the per-cell kernels on the same state, for every tile geometry (13 | 0..12 strided
+    bits), and against the oracle's MPS.measure restatement on the downloaded vector."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    plist = qca_b200.states.plist(state, rules)
+    outs = []
+    for flag in (_lib.QCA_FLAG_PERCELL_MEASURE, _lib.QCA_FLAG_FUSED_MEASURE):
+        eng = _lib.ExactEngine(rules, flags=flag | _lib.QCA_FLAG_LOOSE_BOUND)
+        eng.set_product_state(plist)
+        eng.step(1.0, 2)
+        assert eng.stats()["planes"] == 1
+        before = eng.stats()["kernel_launches"]
+        outs.append(eng.measure())
+        launches = eng.stats()["kernel_launches"] - before
+        assert launches == (2 * n if flag == _lib.QCA_FLAG_PERCELL_MEASURE else 2 * eng.stats()["passes_per_apply"])
+        if flag == _lib.QCA_FLAG_FUSED_MEASURE and n <= 18:
+            pop_o, dpop_o, ent_o, bond_o = oracle.measure_vector(eng.get_state(), n)
+            assert np.abs(outs[-1][0] - pop_o).max() < 1e-12 and np.abs(outs[-1][2] - ent_o).max() < 1e-10
+        eng.close()
+    for a, b in zip(*outs):
+        assert np.abs(a - b).max() < 1e-12

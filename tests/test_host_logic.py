@@ -212,3 +212,21 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("nbits", [13, 15, 18])
+def test_fused_measurement_decomposition(nbits):
+    """The thread/row decomposition of csrc/qca_measure.cu (pass_model.measure_tiles_model) yields, over the
+    tile passes of a register, the sums (s0, s1, w) of every index bit exactly once."""
+    rng = np.random.default_rng(nbits)
+    vec = rng.standard_normal(1 << nbits)
+    seen = {}
+    for ps in _lib.plan_passes(nbits):
+        for g, s0, s1, w in pass_model.measure_tiles_model(vec, ps):
+            assert g not in seen
+            seen[g] = (s0, s1, w)
+    assert sorted(seen) == list(range(nbits))
+    for g, (s0, s1, w) in seen.items():
+        t = vec.reshape(-1, 2, 1 << g)
+        assert abs(s0 - (t[:, 0, :] ** 2).sum()) < 1e-9 and abs(s1 - (t[:, 1, :] ** 2).sum()) < 1e-9
+        assert abs(w - (t[:, 0, :] * t[:, 1, :]).sum()) < 1e-9
