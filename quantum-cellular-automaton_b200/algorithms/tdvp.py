@@ -307,10 +307,14 @@ class TDVP(Algorithm):
         # tail norm is under eps (tdvp.py:290-292) always lies inside the resolved part
         eps = self.args.svd_epsilon
         cap = min(self.args.max_bond_dim, 2 * min(dl, dr))
-        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))), need=cap, tail_floor=eps)
-        tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
-        below = (tail < eps).nonzero()
-        keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
+        info = {}
+        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))), need=cap, tail_floor=eps, info=info)
+        if info.get("decided"):
+            keep = cap       # everything beyond the cap still weighs >= eps: no need to look at the tail (no host sync)
+        else:
+            tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
+            below = (tail < eps).nonzero()
+            keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
         ul = u.reshape(2, dl, -1)[:, :, :keep]
         vr = vh.reshape(-1, 2, dr).permute(1, 0, 2)[:, :keep, :]
         sk = s[:keep] / torch.linalg.vector_norm(s[:keep])

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 from . import _lib
 
@@ -26,7 +27,7 @@ def householder_qr(mat, complete: bool = False):
 
 
 def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels: int = 6, need: int | None = None,
-             tail_floor: float = 0.0):
+             tail_floor: float = 0.0, info: dict | None = None):
     """Thin SVD of a complex128 CUDA matrix from Hermitian eigendecompositions of Gram matrices.
 
     cuSOLVER's SVD of a 512 x 512 complex128 matrix takes 60-130 ms on a B200 and was 88 % of a
@@ -43,7 +44,8 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     through `rest_norm`, the Frobenius norm of the unresolved part.
     need / tail_floor: once `need` singular values are resolved and everything beyond them (resolved
     or not) still has Frobenius norm >= tail_floor, the caller's truncation is decided -- it keeps
-    exactly `need` (the bond cap; tdvp.py:289-293) -- and the deeper levels are skipped.
+    exactly `need` (the bond cap; tdvp.py:289-293) -- and the deeper levels are skipped; `info["decided"]` tells
+    the caller so (it can then skip its own look at the tail).
 
     Returns (u, s, vh, rest_norm): s descending, u[:, i] = mat @ v_i / s_i, mat ~= u diag(s) vh
     up to rest_norm.
@@ -51,11 +53,12 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     import torch
     m, n = mat.shape
     if m < n:  # work on the side with the smaller Gram matrix
-        u, s, vh, rest = gram_svd(mat.conj().T, stop_below, level_ratio, max_levels, need, tail_floor)
+        u, s, vh, rest = gram_svd(mat.conj().T, stop_below, level_ratio, max_levels, need, tail_floor, info)
         return vh.conj().T, s, u.conj().T, rest
     basis = None          # right-singular subspace still to be resolved (n x k), None = everything
     us, ss, vs = [], [], []
     rest_norm = torch.zeros((), dtype=torch.float64, device=mat.device)
+    resolved, sigma1 = 0, 0.0
     for level in range(max_levels):
         work = mat if basis is None else mat @ basis
         gram = work.conj().T @ work
@@ -63,12 +66,21 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
         lam, vec = torch.linalg.eigh(gram)
         lam, vec = lam.flip(0).clamp_min(0.0), vec.flip(1)
         sig = torch.sqrt(lam)
-        top = float(sig[0])                                   # the one host sync of a level
+        # everything the host needs from this level in ONE read: the top value, how many values the level
+        # accepts, and (from the Gram eigenvalues, i.e. only down to ~1e-8 sigma_1) the weight of
+        # whatever lies beyond the first `need` values
+        accept = sig >= level_ratio * sig[0]
+        beyond_from = max((need if need is not None else 0) - resolved, 0)
+        idx = torch.arange(sig.shape[0], device=mat.device)
+        host_vals = torch.stack([sig[0], accept.sum().to(torch.float64), (lam * (~accept | (idx >= beyond_from))).sum()])
+        top, keep_f, tail2_cheap = host_vals.tolist()                # the one host sync of a level
+        if level == 0:
+            sigma1 = top
         if level > 0 and top < stop_below:
             rest_norm = torch.linalg.vector_norm(work)
             break
         last = level == max_levels - 1
-        keep = sig.shape[0] if (last or top == 0.0) else int((sig >= level_ratio * top).sum())
+        keep = sig.shape[0] if (last or top == 0.0) else int(keep_f)
         v_here = vec if basis is None else basis @ vec
         b = work @ vec[:, :keep]
         s_here = torch.linalg.vector_norm(b, dim=0)           # more accurate than sqrt(lam) at the level's bottom
@@ -76,15 +88,23 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
         us.append(b / safe)
         ss.append(s_here)
         vs.append(v_here[:, :keep])
+        resolved += keep
         if keep == sig.shape[0]:
             break
         basis = v_here[:, keep:]
-        resolved = sum(x.shape[0] for x in ss)
         if need is not None and resolved >= need:
-            rest = torch.linalg.vector_norm(mat @ basis)
+            if tail2_cheap > 0.0 and math.sqrt(tail2_cheap) >= max(tail_floor, 1e-6 * sigma1):
+                # far above the resolution of the Gram eigenvalues: the truncation is decided
+                rest_norm = torch.sqrt((lam[keep:]).sum())
+                if info is not None:
+                    info["decided"] = True
+                break
+            rest = torch.linalg.vector_norm(mat @ basis)      # accurate route (one more host sync)
             beyond = torch.cat(ss)[need:]
-            if float(torch.sqrt((beyond * beyond).sum() + rest * rest)) >= tail_floor:   # one more host sync
+            if float(torch.sqrt((beyond * beyond).sum() + rest * rest)) >= tail_floor:
                 rest_norm = rest
+                if info is not None:
+                    info["decided"] = True
                 break
     u, s, v = torch.cat(us, dim=1), torch.cat(ss), torch.cat(vs, dim=1)
     order = torch.argsort(s, descending=True, stable=True)    # levels are ordered; ties inside noise only

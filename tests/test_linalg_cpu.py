@@ -62,3 +62,19 @@ def test_gram_svd_skips_levels_once_the_bond_cap_decides_the_truncation():
     # when the tail beyond `need` is lighter than the floor the spectrum is resolved as before
     u2, s2, vh2, rest2 = gram_svd(torch.as_tensor(a), stop_below=1e-16, need=need, tail_floor=1.0)
     assert len(s2) == 128
+
+
+def test_gram_svd_reports_a_decided_truncation():
+    rng = np.random.default_rng(4)
+    sigma = np.exp(-np.arange(96) * 20.0 / 96)
+    a = matrix_with_spectrum(96, 96, sigma, rng)
+    info = {}
+    u, s, vh, rest = gram_svd(torch.as_tensor(a), stop_below=1e-16, need=10, tail_floor=1e-14, info=info)
+    assert info.get("decided") and len(s) >= 10 and np.abs(s.numpy()[:10] - sigma[:10]).max() < 1e-13
+    # exact rank below `need`: nothing is decided by the cap, the caller looks at the tail itself
+    low = matrix_with_spectrum(96, 96, np.concatenate([sigma[:6], np.zeros(90)]), rng)
+    info = {}
+    u, s, vh, rest = gram_svd(torch.as_tensor(low), stop_below=1e-16, need=10, tail_floor=1e-14, info=info)
+    assert not info.get("decided")
+    tail = np.sqrt(np.cumsum((s.numpy() ** 2)[::-1])[::-1] + float(rest) ** 2)
+    assert (tail < 1e-12).nonzero()[0][0] == 6
