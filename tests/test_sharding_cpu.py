@@ -209,7 +209,8 @@ def test_sharded_engine_refuses_without_device():
 
 
 @pytest.mark.parametrize("world,n,d,lo,hi", [(2, 18, 2, 2, 4), (2, 20, 1, 1, 2), (4, 19, 2, 2, 4), (4, 22, 1, 1, 2),
-                                             (8, 18, 1, 1, 2), (8, 20, 2, 2, 4), (8, 22, 1, 1, 2), (8, 26, 2, 2, 4)])
+                                             (8, 18, 1, 1, 2), (8, 20, 2, 2, 4), (8, 22, 1, 1, 2), (8, 26, 2, 2, 4),
+                                             (2, 30, 2, 2, 4), (4, 30, 2, 2, 4), (8, 30, 2, 2, 4), (8, 33, 2, 2, 4)])
 @pytest.mark.parametrize("rd", [4, 6])
 def test_fast_kernel_remote_slot_bookkeeping(world, n, d, lo, hi, rd):
     """Statement-by-statement model of the remote operand slots of the fast tile-pass kernel
