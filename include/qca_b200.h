@@ -179,8 +179,11 @@ int32_t qca_exact_apply_h(qca_exact_t h, const double* in, double* out, uint64_t
 int32_t qca_exact_norm2(qca_exact_t h, double* norm2);
 
 /* The engine scales H by a bound R of its spectral radius: min(Gershgorin, sum of block norms found
- * by Lanczos on the device at creation).  Sharded engines must agree on R: set the maximum over
- * ranks with this call before the first step. */
+ * by Lanczos on the device at creation; a block whose Lanczos run did not converge leaves the provable
+ * Gershgorin bound in force).  The number of Chebyshev terms of a step -- and with it the number of
+ * cross-rank barriers -- follows from R, so sharded engines MUST agree on it: qca_exact_step fails with
+ * QCA_ERR_STATE on a sharded engine until this call has set the common value (the maximum of
+ * qca_exact_get_stats().spectral_bound over all ranks). */
 int32_t qca_exact_set_spectral_bound(qca_exact_t h, double bound);
 
 typedef struct qca_exact_stats {

@@ -274,3 +274,125 @@ def run_exact(name_or_plist, ncells: int, distance: int, lo: int, hi: int,
         pops.append(p), dpops.append(d), ents.append(e), bonds.append(b)
         psi = exact_step(u, psi)
     return (np.array(pops), np.array(dpops), np.array(ents), np.array(bonds), psi)
+
+
+# ----------------------------------------------------------------------------
+# Matrix-free restatement of H (for registers too large for a dense matrix)
+# ----------------------------------------------------------------------------
+
+def rule_activity(xs: np.ndarray, ncells: int, distance: int, lo: int, hi: int) -> np.ndarray:
+    """act[x] bit (ncells-1-cell) = [# alive neighbours of `cell` within `distance` in [lo, hi)]
+    for every basis state in ``xs``: the predicate of ``rule_hamiltonian_direct`` (the count test the
+    automaton of mpo.py:126-149 encodes, dead cells beyond both ends mpo.py:181-200) as bit words."""
+    xs = np.asarray(xs, dtype=np.int64)
+    act = np.zeros_like(xs)
+    for cell in range(ncells):
+        count = np.zeros_like(xs)
+        for off in range(1, distance + 1):
+            for nb in (cell - off, cell + off):
+                if 0 <= nb < ncells:
+                    count += (xs >> (ncells - 1 - nb)) & 1
+        act |= ((count >= lo) & (count < hi)).astype(np.int64) << (ncells - 1 - cell)
+    return act
+
+
+def apply_h(v: np.ndarray, ncells: int, distance: int, lo: int, hi: int) -> np.ndarray:
+    """H @ v without the matrix: (H v)[x] = sum_cells [P_cell(x)] v[x ^ bit_cell].
+
+    Same operator as ``mpo_as_matrix(mpo_tensors(...))`` (= the reference's ``MPO.as_matrix``,
+    mpo.py:221-230); ``tests/test_oracle_golden.py`` checks it against the reference's own ``H @ v``
+    fixtures and against the dense matrix for every N <= 11 case.  P_cell does not depend on the
+    cell's own bit, so the predicate at x and at the flipped partner agree (H is symmetric)."""
+    v = np.asarray(v)
+    xs = np.arange(1 << ncells, dtype=np.int64)
+    act = rule_activity(xs, ncells, distance, lo, hi)
+    out = np.zeros_like(v)
+    for bit in range(ncells):
+        on = ((act >> bit) & 1).astype(bool)
+        out[on] += v[xs[on] ^ (1 << bit)]
+    return out
+
+
+def exact_step_matrix_free(psi: np.ndarray, ncells: int, distance: int, lo: int, hi: int,
+                           step_size: float, tol: float = 1e-16) -> np.ndarray:
+    """exp(-i pi/2 step_size H) psi by the Taylor series with ``apply_h`` (scaling by halving so
+    that every sub-step has |t| * N <= 1: plain series, no cancellation).  Used where the dense
+    ``calculate_U`` (lautils.py:45-55) does not fit; checked against it in the CPU suite."""
+    t = (np.pi / 2) * step_size
+    pieces = max(1, int(np.ceil(abs(t) * ncells)))
+    dt = t / pieces
+    out = np.array(psi, dtype=complex)
+    for _ in range(pieces):
+        term = out.copy()
+        acc = out.copy()
+        for k in range(1, 200):
+            term = (-1j * dt / k) * apply_h(term, ncells, distance, lo, hi)
+            acc += term
+            if np.abs(term).max() < tol:
+                break
+        out = acc
+    return out
+
+
+# ----------------------------------------------------------------------------
+# The reference's actual measurement route (what its CPU time goes into)
+# ----------------------------------------------------------------------------
+
+def vector_to_mps(psi: np.ndarray) -> list[np.ndarray]:
+    """Successive reduced QRs from the left; mps.py:55-73 (``MPS.from_vector``).
+    Tensors are (physical, left bond, right bond)."""
+    tensors = []
+    rest = np.array(psi, dtype=complex).reshape(2, -1)
+    while rest.shape[1] > 1:
+        q, r = np.linalg.qr(rest)
+        tensors.append(q.reshape(-1, 2, r.shape[0]).transpose(1, 0, 2))
+        rest = r.reshape(r.shape[0] * 2, -1)
+    tensors.append(rest.reshape(-1, 2, 1).transpose(1, 0, 2))
+    return tensors
+
+
+def _fit(a: np.ndarray, shape) -> np.ndarray:
+    """Zero-pad / cut to ``shape`` (MPS.truncate_and_pad_into_shape as used by mps.py:146-181)."""
+    out = np.zeros(shape, dtype=a.dtype)
+    cut = tuple(slice(0, min(s, t)) for s, t in zip(a.shape, shape))
+    out[cut] = a[cut]
+    return out
+
+
+def measure_via_mps(psi: np.ndarray, ncells: int):
+    """``Exact.psi`` -> ``MPS.measure`` exactly as the reference does it (exact.py:19-20,
+    mps.py:100-140): build the MPS by QR, move the orthogonality centre to site 0 by right-QRs
+    (mps.py:183-192), then per site the 2x2 density matrix, the population, the entropy through
+    ``scipy.linalg.logm`` and one left-QR to shift the centre.  Slower than ``measure_vector`` and
+    equal to it to round-off; this is the routine the CPU baseline times."""
+    from scipy.linalg import logm
+    import warnings
+    a = vector_to_mps(psi)
+    n = len(a)
+    assert n == ncells
+    bonds = np.array([float(t.shape[1]) for t in a] + [float(a[-1].shape[2])])
+    for i in range(n - 1, 0, -1):  # make_site_canonical(0): orthonormalize_right_qr, mps.py:164-181
+        t = a[i]
+        s = t.shape
+        q, r = np.linalg.qr(t.transpose(0, 2, 1).reshape(s[0] * s[2], s[1]))
+        q = _fit(q.reshape(s[0], s[2], -1).transpose(0, 2, 1), s)
+        r = _fit(r.T, (a[i - 1].shape[2], s[1]))
+        a[i - 1] = np.tensordot(a[i - 1], r, (2, 0))
+        a[i] = q
+    pop, dpop, ent = np.zeros(n), np.zeros(n), np.zeros(n)
+    for site in range(n):
+        if site > 0:  # orthonormalize_left_qr(site - 1), mps.py:146-162
+            t = a[site - 1]
+            s = t.shape
+            q, r = np.linalg.qr(t.reshape(s[0] * s[1], s[2]))
+            a[site - 1] = _fit(q.reshape(s[0], s[1], -1), s)
+            r = _fit(r, (s[2], a[site].shape[1]))
+            a[site] = np.tensordot(r, a[site], (1, 1)).transpose(1, 0, 2)
+        t = a[site]
+        rho = np.tensordot(t, t.conj(), ((1, 2), (1, 2)))
+        pop[site] = rho[1, 1].real
+        dpop[site] = np.round(pop[site])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ent[site] = (-np.trace(rho @ (logm(rho) / np.log(2)))).real
+    return pop, dpop, ent, bonds

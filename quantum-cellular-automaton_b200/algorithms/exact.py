@@ -14,6 +14,28 @@ from .. import _lib, sharding
 from ..tensor_networks import MPS, MPO
 
 
+def _product_plist(mps, ncells: int):
+    """Alive probabilities of a bond-dimension-1 MPS whose tensors are real, non-negative amplitudes
+    (sqrt(1-p), sqrt(p)) -- what MPS.from_density_distribution (mps.py:35-52) builds -- read from the
+    tensors THEMSELVES (``MPS.A`` is a public list that callers may modify after construction; a cached
+    ``plist`` could be stale).  None for anything else: the caller then merges the tensors on the host."""
+    tensors = getattr(mps, "A", None)
+    if tensors is None or len(tensors) != ncells:
+        return None
+    plist = []
+    for t in tensors:
+        t = np.asarray(t)
+        if t.shape != (2, 1, 1):
+            return None
+        a0, a1 = complex(t[0, 0, 0]), complex(t[1, 0, 0])
+        if a0.imag != 0.0 or a1.imag != 0.0 or a0.real < 0.0 or a1.real < 0.0:
+            return None
+        if abs(a0.real ** 2 + a1.real ** 2 - 1.0) > 1e-15:
+            return None
+        plist.append(min(1.0, a1.real ** 2) if a1.real ** 2 >= 0.5 else 1.0 - min(1.0, a0.real ** 2))
+    return plist
+
+
 class Exact(Algorithm):
 
     def __init__(self, psi_0: MPS, H: MPO, args, *, device: int = 0, stream: int | None = None,
@@ -46,8 +68,8 @@ class Exact(Algorithm):
     @psi.setter
     def psi(self, value: MPS) -> None:
         """exact.py:22-24."""
-        plist = getattr(value, "plist", None)
-        if plist is not None and len(plist) == self._engine.ncells:
+        plist = _product_plist(value, self._engine.ncells)
+        if plist is not None:
             self._engine.set_product_state(plist)  # built on the device, no 2^N host vector
         else:
             self._engine.set_state(value.as_vector())

@@ -43,6 +43,8 @@ from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
 KRYLOV_TOL = 1e-16
+KRYLOV_MAX = 64           # HE_MAXK of csrc/qca_heff.cu
+SVD_EPSILON_FLOOR = 1e-14  # the device SVD resolves singular values to ~1e-15 sigma_1 ABSOLUTE: a cut-off below this keeps noise
 
 
 def _torch():
@@ -54,10 +56,32 @@ def krylov_dimension(rho: float) -> int:
     """Smallest m with (rho/2)^m / m! below KRYLOV_TOL (error bound of the m-step Lanczos
     approximation of exp(-i t H) v for |t| * ||H|| = rho)."""
     m, term = 1, rho / 2.0
-    while term > KRYLOV_TOL and m < 64:
+    while term > KRYLOV_TOL and m < 4 * KRYLOV_MAX:
         m += 1
         term *= (rho / 2.0) / m
     return max(m + 1, 4)
+
+
+def krylov_substeps(rho: float) -> int:
+    """Number of equal pieces a step of |t| * ||H|| = rho is cut into so that every piece meets
+    KRYLOV_TOL with at most KRYLOV_MAX Lanczos vectors (rho up to ~26 needs one piece)."""
+    k = 1
+    while krylov_dimension(rho / k) > KRYLOV_MAX:
+        k += 1
+    return k
+
+
+def mpo_norm_bound(tensors) -> float:
+    """Upper bound of ||H|| for an arbitrary MPO W[i][a,b,wl,wr]: triangle inequality over the
+    operator strings, i.e. the same chain of matrices with every 2x2 block replaced by its operator
+    norm.  Loose (every string counts separately) but safe; used when H is not the rule Hamiltonian,
+    whose tight bound comes from qca_spectral_bound."""
+    vec = None
+    for w in tensors:
+        w = np.asarray(w)
+        m = np.linalg.norm(w.transpose(2, 3, 0, 1), ord=2, axis=(2, 3))    # (wl, wr)
+        vec = m if vec is None else vec @ m
+    return float(np.trace(vec)) if vec.shape[0] == vec.shape[1] else float(vec.sum())
 
 
 class TDVP(Algorithm):
@@ -73,8 +97,14 @@ class TDVP(Algorithm):
         self._W = [torch.as_tensor(np.ascontiguousarray(w), dtype=self.ct, device=self.dev) for w in H.W]
         self._W_host = [np.ascontiguousarray(w, dtype=np.complex128) for w in H.W]
         self._ops: dict = {}      # site operators of the native H_eff, built on first use (H is constant)
-        # ||H_eff|| <= ||H|| <= R: the Krylov dimension follows from |delta| * pi/2 * R
-        self._bound = _lib.spectral_bound(args.rules)
+        # ||H_eff|| <= ||H|| <= R: the Krylov dimension follows from |delta| * pi/2 * R.  R of the rule
+        # Hamiltonian is tight (qca_spectral_bound); any other MPO gets the string-count bound
+        is_rule_h = MPO.hamiltonian_from_rules(args.rules).same_operator_as(H if isinstance(H, MPO) else MPO(list(H.W)))
+        self._bound = _lib.spectral_bound(args.rules) if is_rule_h else mpo_norm_bound(H.W)
+        if args.algorithm == "2tdvp" and not args.svd_epsilon >= SVD_EPSILON_FLOOR:
+            raise ValueError(
+                f"--svd-epsilon {args.svd_epsilon} is below the resolution of the device SVD "
+                f"({SVD_EPSILON_FLOOR}: singular values are accurate to ~1e-15 of the largest, absolutely, not relatively)")
         super().__init__(psi_0, H, args)
         n = len(self._A)
         self._canonicalize(n - 1)  # tdvp.py:23-26: fix the bond dimensions, then right-orthonormal form
@@ -278,13 +308,16 @@ class TDVP(Algorithm):
             lam, vec = torch.linalg.eigh(h)
             phase = torch.exp(-1j * t * lam)
             return ((vec * phase) @ (vec.conj().T @ psi.reshape(-1))).reshape(psi.shape)
-        m = min(krylov_dimension(abs(t) * self._bound), dim)
+        pieces = krylov_substeps(abs(t) * self._bound)   # 1 unless |t| * R > ~26 (large --step-size on long chains)
+        m = min(krylov_dimension(abs(t) * self._bound / pieces), KRYLOV_MAX, dim)
         dl, dr = left.shape[0], right.shape[0]
-        self.heff_applications += m
+        self.heff_applications += m * pieces
         # FP64 operations of the two tensor-core contractions L.psi and T.R (8 per complex MAC); MPO channels
         # that are structurally zero are neither computed nor counted
-        self.heff_flops += m * 8.0 * (op.cols_used * dl * dl * dr + op.rows_used * dl * dr * dr)
-        return heff_expm(left, right, op, psi, m, t, spectral_bound=self._bound).reshape(psi.shape)
+        self.heff_flops += pieces * m * 8.0 * (op.cols_used * dl * dl * dr + op.rows_used * dl * dr * dr)
+        for _ in range(pieces):
+            psi = heff_expm(left, right, op, psi, m, t / pieces, spectral_bound=self._bound).reshape(psi.shape)
+        return psi
 
     def _evolve_site(self, site, delta):
         left, right, w = self._env_left(site - 1), self._env_right(site + 1), self._W[site]

@@ -253,6 +253,7 @@ struct Engine {
     double* peer_plane[kMaxWorld][3][2] = {};
     unsigned long long* peer_flags[kMaxWorld] = {};
     bool peers_ready = false;
+    bool bound_agreed = false;  // sharded: the ranks have been given one common spectral bound (qca_exact_set_spectral_bound)
     bool loopback = false;   // profiling aid: "partners" are this rank's own planes, no cross-rank barrier
     unsigned long long epoch = 0;
     // stats
@@ -717,8 +718,12 @@ static double tridiag_top_eigenvalue(const std::vector<double>& b) {
 }
 
 // Norm of the block operator on a register of `nsites` qubits with flipped qubits `centers`.
+// *converged: the top Ritz value settled (relative change <= 1e-10 over 8 further Lanczos vectors, or the
+// Krylov space closed).  A Ritz value approaches the norm from BELOW, so an unconverged one must not be
+// used as a bound: the caller then keeps the provable Gershgorin bound.
 static int32_t block_norm(const qca_rule_t& rule, int nsites, unsigned long long centers, int device,
-                          double* norm_out, uint64_t* launches) {
+                          double* norm_out, bool* converged, uint64_t* launches) {
+    *converged = false;
     qca_rule_t sub = rule;
     sub.ncells = nsites;
     qca_exact_t h = nullptr;
@@ -753,14 +758,14 @@ static int32_t block_norm(const qca_rule_t& rule, int nsites, unsigned long long
             double n2 = 0.0;
             if ((rc = qca_exact_norm2(h, &n2))) break;
             const double bn = sqrt(n2);
-            if (!(bn > 1e-12)) break;  // invariant subspace: the Ritz values are exact
+            if (!(bn > 1e-12)) { *converged = true; break; }  // invariant subspace: the Ritz values are exact
             beta.push_back(bn);
             if ((rc = launch_scale(e, prev, prev, 1.0 / bn))) break;
             std::swap(prev, cur);      // cur = q_{j+1}, prev = q_j
             bj = bn;
             if ((j % 8) == 7 || j == kLanczosMax - 1) {
                 theta = tridiag_top_eigenvalue(beta);
-                if (theta_old > 0 && fabs(theta - theta_old) <= 1e-10 * theta) break;
+                if (theta_old > 0 && fabs(theta - theta_old) <= 1e-10 * theta) { *converged = true; break; }
                 theta_old = theta;
             }
         }
@@ -773,6 +778,7 @@ static int32_t block_norm(const qca_rule_t& rule, int nsites, unsigned long long
     return rc;
 }
 
+// *bound is left untouched (the caller's provable bound stands) unless every block norm converged.
 static int32_t tight_spectral_bound(const qca_rule_t& rule, int device, double* bound) {
     const int n = rule.ncells, d = rule.distance;
     // fewest blocks such that every block register fits kBoundSites qubits
@@ -799,7 +805,9 @@ static int32_t tight_spectral_bound(const qca_rule_t& rule, int device, double* 
             const int ctx_high = (kind == 0) ? 0 : d;
             const int sites = ctx_low + B + ctx_high;
             const unsigned long long centers = ((1ull << B) - 1ull) << ctx_low;
-            QCA_CHECK(block_norm(rule, sites, centers, device, &val, nullptr));
+            bool converged = false;
+            QCA_CHECK(block_norm(rule, sites, centers, device, &val, &converged, nullptr));
+            if (!converged) return QCA_OK;   // keep the Gershgorin bound rather than trust a lower estimate
             cache.emplace_back(key, val);
         }
         total += val;
@@ -890,7 +898,10 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     if (!(flags & QCA_FLAG_LOOSE_BOUND)) {
         double tight = e->bound;
         if (int32_t rc = qca::tight_spectral_bound(*rule, device, &tight)) { qca_exact_destroy(h); return rc; }
-        QCA_CUDA(cudaSetDevice(device));
+        if (cudaSetDevice(device) != cudaSuccess) {
+            qca::set_error("cudaSetDevice(%d) failed after the spectral-bound computation", device);
+            qca_exact_destroy(h); return QCA_ERR_CUDA;
+        }
         if (tight < e->bound) e->bound = tight;
         e->st.spectral_bound = e->bound;
     }
@@ -1005,6 +1016,10 @@ int32_t qca_exact_step(qca_exact_t h, double step_size, int32_t nsteps) {
     QCA_REQUIRE(e->nplanes > 0 && e->resolved, QCA_ERR_STATE, "step before a state was set (and resolved)");
     QCA_REQUIRE(nsteps >= 0, QCA_ERR_ARG, "nsteps must be >= 0");
     QCA_REQUIRE(isfinite(step_size), QCA_ERR_ARG, "step_size must be finite");
+    // every rank derives the number of Chebyshev terms -- hence of cross-rank barriers -- from R: ranks that
+    // computed R independently could disagree in the last digits and dead-lock
+    QCA_REQUIRE(e->world == 1 || e->loopback || e->bound_agreed, QCA_ERR_STATE,
+                "sharded engine: call qca_exact_set_spectral_bound with the maximum over all ranks before stepping");
     QCA_CUDA(cudaSetDevice(e->device));
     for (int s = 0; s < nsteps; ++s) QCA_CHECK(qca::step_once(e, step_size));
     return QCA_OK;
@@ -1095,6 +1110,7 @@ int32_t qca_exact_set_spectral_bound(qca_exact_t h, double bound) {
     QCA_REQUIRE(h, QCA_ERR_ARG, "NULL handle");
     QCA_REQUIRE(bound > 0.0 && isfinite(bound), QCA_ERR_ARG, "spectral bound must be positive");
     h->e.bound = bound;
+    h->e.bound_agreed = true;
     h->e.st.spectral_bound = bound;
     return QCA_OK;
 }

@@ -66,6 +66,10 @@ class Args:
         p.add_argument("--svd-epsilon", dest="SVD_EPSILON", type=float, default=0.00005)
         p.add_argument("--plotting-frequency", dest="PLOTTING_FREQUENCY", type=float, default=1.0)
         a, _ = p.parse_known_args(argv)
+        if a.ALGORITHM == "a1tdvp":
+            # the flag value exists in the reference (parser.py:77-83); its adaptive bond-dimension heuristics
+            # (tdvp.py:190-268, marked experimental there) are outside the B200 path
+            p.error("--algorithm a1tdvp is not implemented on the B200 path (use exact, 1tdvp or 2tdvp)")
         return cls(
             rules=Rules(ncells=a.NUM_CELLS, activation_interval=range(a.INTERVAL[0], a.INTERVAL[1]),
                         distance=a.DISTANCE, periodic=False),

@@ -33,6 +33,11 @@ EXACT_CASES = [
     ("exact_fullblinker10_d2", 10, 2, 1, 3, "full_blinker", 1000, 0.005, 1.0),
     ("exact_outer7_d3", 7, 3, 2, 5, "all_ket_1_but_outer", 1000, 0.005, 1.0),
     ("exact_single2", 2, 1, 1, 2, "single", 800, 0.005, 1.0),            # smallest chain
+    # registers of >= 13 qubits: the sizes at which the B200 path runs its fast tile-pass kernel
+    # (pass_kernel_v2), the Clenshaw stepper and the fused measurement -- dense 8192^2 / 16384^2 eigh
+    # in the reference, minutes on the build box
+    ("exact_triple13_d2", 13, 2, 2, 4, "triple_blinker", 1200, 0.005, 1.0),  # configs[3] rule, one tile pass
+    ("exact_blinker14", 14, 1, 1, 2, "blinker", 800, 0.005, 1.0),            # configs[1] rule, two tile passes
 ]
 
 TDVP_CASES = [
