@@ -71,6 +71,27 @@ static void apply_h_axpy(const cplx* v, cplx* out, int n, int d, int lo, int hi,
     }
 }
 
+/* Rows [x0, x0 + count) of H v only: out[i] = (H v)[x0 + i].  A bounded sample of one operator application
+ * on a register whose full application takes minutes on the host (bench.py, CPU legs). */
+int qo_apply_h_rows(const double* v_, double* out_, int n, int d, int lo, int hi, uint64_t x0, uint64_t count) {
+    if (n < 1 || n > 40 || d < 1 || x0 + count > (1ull << n)) return 1;
+    const cplx* v = (const cplx*)v_;
+    cplx* out = (cplx*)out_;
+#pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t x = x0 + i;
+        double sr = 0.0, si = 0.0;
+        for (int cell = 0; cell < n; ++cell) {
+            if (cell_active(x, cell, n, d, lo, hi)) {
+                const cplx p = v[x ^ (1ull << (n - 1 - cell))];
+                sr += p.re; si += p.im;
+            }
+        }
+        out[i].re = sr; out[i].im = si;
+    }
+    return 0;
+}
+
 int qo_apply_h(const double* v, double* out, int n, int d, int lo, int hi) {
     if (n < 1 || n > 40 || d < 1) return 1;
     apply_h_axpy((const cplx*)v, (cplx*)out, n, d, lo, hi, 1.0, NULL, 0.0);

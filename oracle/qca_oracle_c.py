@@ -26,6 +26,7 @@ def lib() -> C.CDLL:
         dp = C.POINTER(C.c_double)
         _lib.qo_set_threads.argtypes = [C.c_int]
         _lib.qo_apply_h.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.qo_apply_h_rows.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
         _lib.qo_step.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         _lib.qo_measure.argtypes = [dp, C.c_int, dp, dp]
         _lib.qo_product_state.argtypes = [dp, C.c_int, dp]
@@ -49,6 +50,38 @@ def apply_h(v: np.ndarray, ncells: int, distance: int, lo: int, hi: int) -> np.n
     if lib().qo_apply_h(_ptr(v), _ptr(out), ncells, distance, lo, hi):
         raise ValueError("qo_apply_h: bad arguments")
     return out
+
+
+def apply_h_rows(v: np.ndarray, ncells: int, distance: int, lo: int, hi: int, x0: int, count: int,
+                 out: np.ndarray | None = None) -> np.ndarray:
+    """Rows [x0, x0 + count) of H @ v (bounded timing sample of one application)."""
+    assert v.dtype == np.complex128 and v.flags.c_contiguous and v.size == 1 << ncells
+    if out is None:
+        out = np.empty(count, dtype=np.complex128)
+    if lib().qo_apply_h_rows(_ptr(v), _ptr(out), ncells, distance, lo, hi, int(x0), int(count)):
+        raise ValueError("qo_apply_h_rows: bad arguments")
+    return out
+
+
+def product_state(ncells: int, plist) -> np.ndarray:
+    psi = np.empty(1 << ncells, dtype=np.complex128)
+    p = np.ascontiguousarray(plist, dtype=np.float64)
+    lib().qo_product_state(_ptr(psi), ncells, _ptr(p))
+    return psi
+
+
+def chebyshev_terms(ncells: int, step_size: float) -> int:
+    """Number of terms qo_step sums for this register and step (one application of H each)."""
+    z = ncells * abs(np.pi / 2 * step_size)
+    # same truncation rule as qo_step, evaluated through scipy's Bessel functions
+    from scipy.special import jv
+    kmax = int(z + 14.0 * np.cbrt(z + 1.0) + 40.0)
+    j = np.abs(jv(np.arange(kmax + 1), z))
+    n, tail = kmax + 1, 0.0
+    while n > 2 and tail + 2.0 * j[n - 1] < 1e-17:
+        tail += 2.0 * j[n - 1]
+        n -= 1
+    return n
 
 
 class Stepper:

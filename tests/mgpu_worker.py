@@ -87,6 +87,29 @@ def main() -> int:
         if ref is not None:
             ref.close()
         dist.barrier()
+    # rows written by the C oracle (tests/golden/make_golden_c.py: matrix-free Hermitian H, Chebyshev series on the
+    # host) at 20..26 qubits: the sharded path against an independent computation, not against this library
+    from conftest import golden_names, load_golden
+    for name in golden_names("cexact"):
+        spec, g = load_golden(name)
+        n = spec["ncells"]
+        if n - rbits < 13:
+            continue
+        rules = qca_b200.Rules(n, range(spec["lo"], spec["hi"]), spec["distance"])
+        eng = sharding.ShardedExactEngine(rules, device=local)
+        eng.set_product_state(qca_b200.states.plist(spec["state"], rules))
+        rows = g["population"].shape[0]
+        for k in range(rows):
+            pop, _, ent, _ = eng.measure()
+            dp, de = np.abs(pop - g["population"][k]).max(), np.abs(ent - g["single_site_entropy"][k]).max()
+            check(f"C-oracle rows {name} row {k}", dp < 1e-10 and de < 1e-10, f"pop {dp:.3e} ent {de:.3e}")
+            if k + 1 < rows:
+                eng.step(float(g["effective_step_size"]), 1)
+        if rank == 0:
+            print(f"mgpu_worker world={world}: {name} {rows} rows vs C oracle checked "
+                  f"({eng.stats()['passes_per_apply']} tile passes, {eng.stats()['local_bits']} local qubits)", flush=True)
+        eng.close()
+        dist.barrier()
     # the Exact plug-in picks the sharded engine up from torch.distributed
     rules = qca_b200.Rules(14 + rbits, range(1, 2), 1)
     algo = qca_b200.Exact(qca_b200.states.make("single", rules), None, qca_b200.Args(rules=rules, step_size=1.0), device=local)

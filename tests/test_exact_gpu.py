@@ -8,9 +8,9 @@ vectors are compared at 1e-11.
 import numpy as np
 import pytest
 
-import pass_model
 import qca_b200
 import qca_oracle as oracle
+import qca_oracle_c as oracle_c
 from conftest import golden_names, load_golden
 from qca_b200 import _lib
 
@@ -68,15 +68,56 @@ def test_apply_h_seeded_vs_oracle(n, d, lo, hi):
     got = eng.apply_h(v)
     if n <= 11:
         want = oracle.rule_hamiltonian_direct(n, d, lo, hi) @ v
-    else:  # matrix-free numpy restatement, itself checked against the dense oracle in the CPU suite
-        xs = np.arange(1 << n, dtype=np.int64)
-        act = pass_model.activity(xs, n, d, lo, hi)
-        want = np.zeros_like(v)
-        for gbit in range(n):
-            on = ((act >> gbit) & 1).astype(bool)
-            want[on] += v[xs[on] ^ (1 << gbit)]
+    else:  # the oracle's matrix-free restatements (pinned to the reference's H @ v fixtures in the CPU suite)
+        want = oracle_c.apply_h(v, n, d, lo, hi)
+        if n <= 16:
+            assert np.abs(oracle.apply_h(v, n, d, lo, hi) - want).max() < 1e-12
     assert np.abs(got - want).max() < 1e-11
     eng.close()
+
+
+@pytest.mark.parametrize("n,d,lo,hi,state,tau", [
+    (13, 1, 1, 2, "single", 1.0), (13, 2, 2, 4, "equal_superposition", 0.37), (14, 2, 2, 4, "triple_blinker", 1.0),
+    (15, 1, 1, 3, "gradient", -0.6), (17, 3, 2, 5, "blinker", 1.0), (18, 2, 2, 4, "triple_blinker", 1.0),
+    (20, 1, 1, 2, "blinker", 1.0), (22, 2, 1, 3, "full_blinker", 0.5)])
+def test_fast_kernel_step_and_measure_vs_c_oracle(n, d, lo, hi, state, tau):
+    """pass_kernel_v2 (>= 13 qubits: one, two and three tile passes) + Clenshaw stepper + fused measurement,
+    stepped against the C oracle (matrix-free Hermitian H, forward Chebyshev series in complex arithmetic;
+    pinned to the reference's N <= 14 runs in tests/test_oracle_golden.py): populations and entropies before
+    every step at 1e-10, the final vector at 1e-11."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    plist = qca_b200.states.plist(state, rules)
+    eng = _lib.ExactEngine(rules)
+    eng.set_product_state(plist)
+    ref = oracle_c.Stepper(n, d, lo, hi)
+    ref.set_product_state(plist)
+    for k in range(3):
+        pop, _, ent, _ = eng.measure()
+        pop_o, ent_o = ref.measure()
+        assert np.abs(pop - pop_o).max() < TOL and np.abs(ent - ent_o).max() < TOL, (k, n)
+        eng.step(tau, 1)
+        ref.step(tau)
+    assert eng.stats()["passes_per_apply"] == (1 if n <= 13 else (2 if n <= 22 else 3))
+    assert np.abs(eng.get_state() - ref.psi).max() < 1e-11
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_names("cexact"))
+def test_exact_plugin_matches_c_oracle_rows(name):
+    """Registers of 20..26 qubits (BASELINE configs[1] and the three-pass geometry of the N = 30 bench)
+    through the Exact plug-in against rows the C oracle wrote (tests/golden/make_golden_c.py)."""
+    spec, g = load_golden(name)
+    rules = make_rules(spec)
+    args = qca_b200.Args(rules=rules, step_size=float(g["effective_step_size"]))
+    algo = qca_b200.Exact(qca_b200.states.make(spec["state"], rules), qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    rows, n = g["population"].shape
+    for k in range(rows):
+        pop, dpop, sse, bond = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n + 1)
+        algo.measure(pop, dpop, sse, bond)
+        assert np.abs(pop - g["population"][k]).max() < TOL, k
+        assert np.abs(sse - g["single_site_entropy"][k]).max() < TOL, k
+        if k + 1 < rows:
+            algo.do_time_step()
 
 
 @pytest.mark.parametrize("state", ["single", "blinker", "equal_superposition", "gradient", "all_ket_1"])
