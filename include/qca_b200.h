@@ -126,6 +126,8 @@ typedef struct qca_exact* qca_exact_t;
 #define QCA_FLAG_FUSED_MEASURE 8u   /* measure with one read of the state per tile pass (csrc/qca_measure.cu; single-plane
                                        states on >= 13 local qubits) instead of one read per cell.  Default on one GPU;
                                        sharded engines opt in with this flag or the environment variable QCA_FUSED_MEASURE */
+#define QCA_FLAG_TILE_PATH_ONLY 32u /* registers <= 13 qubits: use the tile-pass kernels instead of the one-kernel step (tests) */
+#define QCA_FLAG_NO_GRAPH 64u      /* registers of 14..24 qubits: launch a step kernel by kernel instead of replaying its CUDA graph */
 #define QCA_FLAG_PERCELL_MEASURE 16u /* always use the per-cell measurement kernels (also: environment QCA_PERCELL_MEASURE) */
 
 /* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U

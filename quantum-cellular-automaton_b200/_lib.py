@@ -32,6 +32,8 @@ QCA_FLAG_PROFILE = 2
 QCA_FLAG_LOOSE_BOUND = 4
 QCA_FLAG_FUSED_MEASURE = 8
 QCA_FLAG_PERCELL_MEASURE = 16
+QCA_FLAG_TILE_PATH_ONLY = 32
+QCA_FLAG_NO_GRAPH = 64
 QCA_IPC_HANDLE_BYTES = 64
 
 

@@ -18,6 +18,7 @@
 #include "qca_plan.h"
 #include "qca_pass.cuh"
 #include "qca_measure.h"
+#include "qca_small.h"
 
 namespace qca {
 
@@ -253,9 +254,15 @@ struct Engine {
     double* peer_plane[kMaxWorld][3][2] = {};
     unsigned long long* peer_flags[kMaxWorld] = {};
     bool peers_ready = false;
+    bool graph_warm = false;    // an eager step has run (function attributes set, work planes allocated)
     bool bound_agreed = false;  // sharded: the ranks have been given one common spectral bound (qca_exact_set_spectral_bound)
     bool loopback = false;   // profiling aid: "partners" are this rank's own planes, no cross-rank barrier
     unsigned long long epoch = 0;
+    // CUDA graphs of a whole step for launch-bound registers (14..kGraphMaxBits local qubits, one GPU)
+    struct StepGraph { double step_size; int cur, nplanes; double bound; cudaGraphExec_t exec; uint64_t launches, pass_launches;
+                       double pass_bytes; int terms, cur_after; };
+    std::vector<StepGraph> graphs;
+    std::vector<const void*> configured;   // pass kernels whose shared-memory attribute has been set
     // stats
     qca_exact_stats_t st{};
     struct ProfiledLaunch { cudaEvent_t ev0, ev1; int pass; };
@@ -264,8 +271,15 @@ struct Engine {
     size_t plane_bytes() const { return (size_t)namps * sizeof(double); }
 };
 
+// captured steps hold the plane addresses: drop them whenever a plane comes or goes
+static void invalidate_graphs(Engine* e) {
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+}
+
 static int32_t ensure_plane(Engine* e, int v, int p) {
     if (e->plane[v][p]) return QCA_OK;
+    invalidate_graphs(e);
     cudaError_t err = cudaMalloc(&e->plane[v][p], e->plane_bytes());
     if (err != cudaSuccess) {
         cudaGetLastError();
@@ -278,6 +292,7 @@ static int32_t ensure_plane(Engine* e, int v, int p) {
 
 static void release_plane(Engine* e, int v, int p) {
     if (!e->plane[v][p] || e->world > 1) return;  // sharded planes are exported: never freed
+    invalidate_graphs(e);
     cudaFree(e->plane[v][p]);
     e->plane[v][p] = nullptr;
     e->st.device_bytes -= (double)e->plane_bytes();
@@ -400,7 +415,11 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
                     nunc, a.nrem);
         kern = generic_pass_kernel(wide);
     }
-    QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // (once per kernel and engine: nothing but launches may happen while a step is being captured into a graph)
+    if (std::find(e->configured.begin(), e->configured.end(), (const void*)kern) == e->configured.end()) {
+        QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        e->configured.push_back((const void*)kern);
+    }
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
     dim3 grid(gx, e->nplanes, 1);
     const bool profile = (e->flags & QCA_FLAG_PROFILE) != 0;
@@ -511,6 +530,18 @@ static int32_t step_once(Engine* e, double step_size) {
     QCA_CHECK(chebyshev_plan(z, 1e-15, a));
     const int K = (int)a.size() - 1;  // >= 1
     e->st.last_terms = K + 1;
+    if (e->world == 1 && e->local_bits <= kSmallMaxBits && K + 1 <= kSmallMaxTerms && !(e->flags & QCA_FLAG_TILE_PATH_ONLY)) {
+        // whole step in one kernel, vectors in shared memory (csrc/qca_small.cu)
+        SmallStepArgs sa{};
+        for (int p = 0; p < 2; ++p) { sa.src[p] = e->plane[e->cur][p]; sa.dst[p] = e->plane[e->cur][p]; }
+        sa.nbits = e->local_bits; sa.distance = e->rule.distance; sa.nterms = K + 1;
+        sa.interval_mask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+        sa.gamma = sgn * 2.0 / e->bound; sa.gamma_last = sgn / e->bound;
+        for (int k = 0; k <= K; ++k) sa.coef[k] = a[k];
+        QCA_CHECK(launch_small_step(sa, e->nplanes, e->stream));
+        e->st.kernel_launches += 1;
+        return QCA_OK;
+    }
     QCA_CHECK(ensure_work_planes(e));
     const int P = e->cur;
     int X = (P + 1) % 3, Y = (P + 2) % 3;
@@ -526,6 +557,56 @@ static int32_t step_once(Engine* e, double step_size) {
     }
     QCA_CHECK(apply_operator(e, Y, X, P, a[0], (K == 1) ? -1 : Y, 1.0, sgn / R));
     e->cur = Y;
+    return QCA_OK;
+}
+
+// Registers of 14..kGraphMaxBits qubits on one GPU: a step is 100-200 launches of a few microseconds each, i.e.
+// launch-bound from the host.  The launch sequence of step_once depends only on (step size, resident vector
+// index, planes, bound): it is captured once per such key and replayed as one cudaGraphLaunch.
+constexpr int kGraphMaxBits = 24;
+
+static int32_t step_graphed(Engine* e, double step_size) {
+    const bool eligible = e->world == 1 && e->local_bits > kSmallMaxBits && e->local_bits <= kGraphMaxBits &&
+                          !(e->flags & (QCA_FLAG_PROFILE | QCA_FLAG_NO_GRAPH)) && step_size != 0.0;
+    if (!eligible) return step_once(e, step_size);
+    for (const Engine::StepGraph& g : e->graphs) {
+        if (g.step_size == step_size && g.cur == e->cur && g.nplanes == e->nplanes && g.bound == e->bound) {
+            QCA_CUDA(cudaGraphLaunch(g.exec, e->stream));
+            e->st.kernel_launches += g.launches; e->st.pass_launches += g.pass_launches; e->st.pass_bytes += g.pass_bytes;
+            e->st.last_terms = g.terms; e->cur = g.cur_after;
+            return QCA_OK;
+        }
+    }
+    // first use of this key: make sure nothing inside the capture allocates or configures
+    QCA_CHECK(ensure_work_planes(e));
+    if (e->graphs.size() >= 12) return step_once(e, step_size);   // a caller cycling through step sizes: stay eager
+    Engine::StepGraph g{};
+    g.step_size = step_size; g.cur = e->cur; g.nplanes = e->nplanes; g.bound = e->bound;
+    const qca_exact_stats_t before = e->st;
+    // the function attributes of the pass kernels are set on their first eager launch
+    if (!e->graph_warm) {
+        e->graph_warm = true;
+        return step_once(e, step_size);
+    }
+    QCA_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int32_t rc = step_once(e, step_size);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(e->stream, &graph);
+    if (rc != QCA_OK || end != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc == QCA_OK) set_error("CUDA graph capture of a step failed: %s", cudaGetErrorString(end));
+        return rc != QCA_OK ? rc : QCA_ERR_CUDA;
+    }
+    const cudaError_t inst = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(inst)); return QCA_ERR_CUDA; }
+    g.launches = e->st.kernel_launches - before.kernel_launches;
+    g.pass_launches = e->st.pass_launches - before.pass_launches;
+    g.pass_bytes = e->st.pass_bytes - before.pass_bytes;
+    g.terms = e->st.last_terms; g.cur_after = e->cur;
+    e->graphs.push_back(g);
+    QCA_CUDA(cudaGraphLaunch(g.exec, e->stream));   // the capture recorded the step without running it
     return QCA_OK;
 }
 
@@ -641,13 +722,18 @@ static int32_t measure_partial(Engine* e, double* sums) {
     };
     // fused path (csrc/qca_measure.cu): one read of the state per tile pass instead of one per cell
     const bool fused = (e->flags & QCA_FLAG_FUSED_MEASURE) && e->nplanes == 1 && e->local_bits >= kTile;
+    const bool small = e->world == 1 && e->local_bits <= kSmallMaxBits && !(e->flags & (QCA_FLAG_PERCELL_MEASURE | QCA_FLAG_TILE_PATH_ONLY)) && !fused;
+    if (small) {   // all cells in one launch (csrc/qca_small.cu)
+        QCA_CHECK(launch_small_measure(re, im, e->local_bits, e->d_sums, e->stream));
+        e->st.kernel_launches += 1;
+    }
     if (fused) {
         for (const qca_pass_t& ps : e->passes) {
             QCA_CHECK(measure_tiles(re, e->namps, ps, e->shard, n, e->d_partials, 2 * e->num_sms, e->d_sums, e->stream));
             e->st.kernel_launches += 2;
         }
     }
-    for (int bit = 0; bit < e->local_bits && !fused; ++bit) {
+    for (int bit = 0; bit < e->local_bits && !fused && !small; ++bit) {
         const int cell = n - 1 - global_pos(bit, e->shard);
         const unsigned long long npairs = e->namps >> 1;
         const int blocks = blocks_for(npairs);
@@ -928,6 +1014,7 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& pr : e->prof) { cudaEventDestroy(pr.ev0); cudaEventDestroy(pr.ev1); }
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
     if (e->peers_ready) {
         for (int r = 0; r < e->world; ++r) {
             if (r == e->rank) continue;
@@ -1021,7 +1108,7 @@ int32_t qca_exact_step(qca_exact_t h, double step_size, int32_t nsteps) {
     QCA_REQUIRE(e->world == 1 || e->loopback || e->bound_agreed, QCA_ERR_STATE,
                 "sharded engine: call qca_exact_set_spectral_bound with the maximum over all ranks before stepping");
     QCA_CUDA(cudaSetDevice(e->device));
-    for (int s = 0; s < nsteps; ++s) QCA_CHECK(qca::step_once(e, step_size));
+    for (int s = 0; s < nsteps; ++s) QCA_CHECK(qca::step_graphed(e, step_size));
     return QCA_OK;
 }
 

@@ -307,3 +307,82 @@ def test_fused_measurement_matches_per_cell_kernels_and_oracle(n, d, lo, hi, sta
         eng.close()
     for a, b in zip(*outs):
         assert np.abs(a - b).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,d,lo,hi,state", [(1, 1, 1, 2, "single"), (2, 1, 1, 2, "single"), (5, 2, 1, 3, "blinker"),
+                                             (9, 1, 1, 2, "single"), (12, 2, 2, 4, "triple_blinker"), (13, 1, 1, 3, "gradient")])
+def test_one_kernel_step_equals_tile_pass_path(n, d, lo, hi, state):
+    """Registers of <= 13 qubits take a whole step (and a whole measurement) in one kernel (csrc/qca_small.cu);
+    QCA_FLAG_TILE_PATH_ONLY keeps them on the tile-pass kernels.  Same recurrence: the states agree to
+    round-off, one plane and two, both time directions, and the launch counts show which path ran."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    plist = qca_b200.states.plist(state, rules)
+    rng = np.random.default_rng(n)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    for upload in (None, psi):
+        small, tiles = _lib.ExactEngine(rules), _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_TILE_PATH_ONLY)
+        for eng in (small, tiles):
+            eng.set_product_state(plist) if upload is None else eng.set_state(upload)
+            eng.reset_stats()
+        for tau in (1.0, -0.4, 2.5):
+            small.step(tau, 2), tiles.step(tau, 2)
+            assert np.abs(small.get_state() - tiles.get_state()).max() < 2e-13
+            for a, b in zip(small.measure(), tiles.measure()):
+                assert np.abs(a - b).max() < 1e-12
+        assert small.stats()["planes"] == tiles.stats()["planes"] == (1 if upload is None and state != "gradient" else small.stats()["planes"])
+        # 6 steps + 3 measurements: one launch each (plus the pack kernels of get_state)
+        assert small.stats()["pass_launches"] == 0 and tiles.stats()["pass_launches"] > 0
+        assert abs(small.norm2() - 1.0) < 1e-12
+        small.close(), tiles.close()
+
+
+@pytest.mark.parametrize("name", golden_names("exact"))
+def test_tile_pass_path_matches_reference_run_on_small_registers(name):
+    """The reference's runs again, with the one-kernel step switched off: the generic / fast tile-pass kernels
+    at N <= 14 (the default path of these sizes is covered by test_exact_plugin_matches_reference_run)."""
+    spec, g = load_golden(name)
+    rules = make_rules(spec)
+    eng = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_TILE_PATH_ONLY | _lib.QCA_FLAG_NO_GRAPH)
+    eng.set_product_state(qca_b200.states.plist(spec["state"], rules))
+    for k in range(g["population"].shape[0]):
+        pop, _, ent, _ = eng.measure()
+        assert np.abs(pop - g["population"][k]).max() < TOL and np.abs(ent - g["single_site_entropy"][k]).max() < TOL
+        eng.step(float(g["effective_step_size"]), 1)
+    assert np.abs(eng.get_state() - g["psi_final"]).max() < 1e-11
+    eng.close()
+
+
+@pytest.mark.parametrize("n,d,lo,hi,state", [(14, 1, 1, 2, "blinker"), (16, 2, 2, 4, "triple_blinker"), (20, 1, 1, 2, "blinker")])
+def test_graph_replay_equals_eager_launches(n, d, lo, hi, state):
+    """Registers of 14..24 qubits replay a captured CUDA graph of the step (one per resident-vector index and step
+    size).  Same kernels, same arguments: bit-identical states, identical launch accounting, across enough steps
+    to cycle through all three vector rotations, a change of step size, and a new upload in between."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    plist = qca_b200.states.plist(state, rules)
+    graph, eager = _lib.ExactEngine(rules), _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_NO_GRAPH)
+    for eng in (graph, eager):
+        eng.set_product_state(plist)
+        eng.reset_stats()
+    for tau, count in ((1.0, 7), (0.5, 4), (1.0, 3), (-1.0, 2)):
+        for _ in range(count):
+            graph.step(tau, 1), eager.step(tau, 1)
+        assert np.array_equal(graph.get_state(), eager.get_state())
+        for a, b in zip(graph.measure(), eager.measure()):
+            assert np.array_equal(a, b)
+    sg, se = graph.stats(), eager.stats()
+    for key in ("kernel_launches", "pass_launches", "pass_bytes", "last_terms"):
+        assert sg[key] == se[key], key
+    # a general complex state (two planes) invalidates nothing silently: new graphs, same answers
+    rng = np.random.default_rng(3)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    graph.set_state(psi), eager.set_state(psi)
+    for _ in range(4):
+        graph.step(1.0, 1), eager.step(1.0, 1)
+    assert np.array_equal(graph.get_state(), eager.get_state())
+    graph.set_product_state(plist), eager.set_product_state(plist)   # back to one plane: plane 1 is released
+    for _ in range(4):
+        graph.step(1.0, 1), eager.step(1.0, 1)
+    assert np.array_equal(graph.get_state(), eager.get_state())
+    graph.close(), eager.close()
