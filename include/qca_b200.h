@@ -74,6 +74,12 @@ typedef struct qca_pass {
 /* Plan for a local register of local_bits qubits; returns the number of passes
  * written to passes[0..capacity). */
 int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity, int32_t* npasses);
+/* Plan of the cluster kernels (one GPU, >= 14 qubits): CTA tiles of 14 index bits, joined by up to
+ * max_cluster_bits (<= 3) more through distributed shared memory.  `high_bits` counts the CTA-local strided bits,
+ * `reserved` the cluster bits directly above them; later passes keep at least min_low (>= 4) contiguous low bits.
+ * Returns 0 passes for registers below 14 qubits. */
+int32_t qca_plan_passes_v3(int32_t local_bits, int32_t max_cluster_bits, int32_t min_low, qca_pass_t* passes,
+                           int32_t capacity, int32_t* npasses);
 
 /* Sharded register: global index-bit positions of the log2(world_size) sharded qubits, ascending
  * (rank bit j <-> positions[j]).  Non-adjacent cells {0, d+1, 2(d+1)} when the register is large
@@ -128,6 +134,8 @@ typedef struct qca_exact* qca_exact_t;
                                        sharded engines opt in with this flag or the environment variable QCA_FUSED_MEASURE */
 #define QCA_FLAG_TILE_PATH_ONLY 32u /* registers <= 13 qubits: use the tile-pass kernels instead of the one-kernel step (tests) */
 #define QCA_FLAG_NO_GRAPH 64u      /* registers of 14..24 qubits: launch a step kernel by kernel instead of replaying its CUDA graph */
+#define QCA_FLAG_V2_KERNELS 128u    /* one GPU, >= 14 qubits: use the 13-bit tile-pass kernels (pass_kernel_v2) instead of the
+                                      cluster kernels (pass_kernel_v3); also: environment QCA_V2_KERNELS */
 #define QCA_FLAG_PERCELL_MEASURE 16u /* always use the per-cell measurement kernels (also: environment QCA_PERCELL_MEASURE) */
 
 /* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U

@@ -34,6 +34,7 @@ QCA_FLAG_FUSED_MEASURE = 8
 QCA_FLAG_PERCELL_MEASURE = 16
 QCA_FLAG_TILE_PATH_ONLY = 32
 QCA_FLAG_NO_GRAPH = 64
+QCA_FLAG_V2_KERNELS = 128
 QCA_IPC_HANDLE_BYTES = 64
 
 
@@ -85,6 +86,7 @@ SYMBOLS = {
     "qca_spectral_bound": (C.c_int32, [C.POINTER(RuleStruct), _dp]),
     "qca_chebyshev_plan": (C.c_int32, [C.c_double, C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_passes": (C.c_int32, [C.c_int32, C.POINTER(PassStruct), C.c_int32, C.POINTER(C.c_int32)]),
+    "qca_plan_passes_v3": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(PassStruct), C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_shard": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.POINTER(C.c_int32)]),
     "qca_plan_remote": (C.c_int32, [C.POINTER(RuleStruct), C.c_int32, C.c_int32, C.POINTER(RemoteOpStruct), C.c_int32,
                                     C.POINTER(C.c_int32)]),
@@ -181,6 +183,16 @@ def plan_passes(local_bits: int) -> list[dict]:
     check(lib.qca_plan_passes(local_bits, buf, n.value, C.byref(n)))
     return [dict(low_bits=p.low_bits, high_start=p.high_start, high_bits=p.high_bits, flip_mask=p.flip_mask)
             for p in buf]
+
+
+def plan_passes_v3(local_bits: int, max_cluster_bits: int = 3, min_low: int = 4) -> list[dict]:
+    """Plan of the cluster tile-pass kernels (qca_plan_passes_v3); cluster_bits = the pass's `reserved` field."""
+    n = C.c_int32()
+    check(lib.qca_plan_passes_v3(local_bits, max_cluster_bits, min_low, None, 0, C.byref(n)))
+    buf = (PassStruct * max(n.value, 1))()
+    check(lib.qca_plan_passes_v3(local_bits, max_cluster_bits, min_low, buf, n.value, C.byref(n)))
+    return [dict(low_bits=p.low_bits, high_start=p.high_start, high_bits=p.high_bits, cluster_bits=p.reserved,
+                 flip_mask=p.flip_mask) for p in buf[:n.value]]
 
 
 def plan_remote(rules, world_size: int, rank: int) -> list[dict]:

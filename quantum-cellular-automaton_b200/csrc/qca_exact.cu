@@ -17,6 +17,7 @@
 #include "qca_common.cuh"
 #include "qca_plan.h"
 #include "qca_pass.cuh"
+#include "qca_pass3.cuh"
 #include "qca_measure.h"
 #include "qca_small.h"
 
@@ -223,6 +224,11 @@ struct Engine {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // host <-> device state traffic runs on its own highest-priority stream: its small pack/unpack kernels are
+    // dispatched ahead of the queued CTAs of another engine's tile passes, so the PCIe copies of one state
+    // overlap the kernels of another (bench.py e2e pipeline); ordered against `stream` with events
+    cudaStream_t io_stream = nullptr;
+    cudaEvent_t io_event = nullptr;
     unsigned long long namps = 0;
     ShardMap shard{};     // local index -> global basis-state index
     double* plane[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -249,6 +255,12 @@ struct Engine {
     std::vector<int> win_shift;
     std::vector<unsigned> win_mask;
     bool fast_path = false;
+    // cluster kernels (qca_pass3.cuh): one GPU, >= 14 qubits, distance <= 4
+    bool use_v3 = false;
+    std::vector<qca_pass_t> passes3;
+    struct V3Tables { unsigned short* thr = nullptr; unsigned short* row = nullptr; int thr_shift = 0, thr_pos = 0; unsigned thr_mask = 0;
+                      int row_shift = 0, row_pos = 0; unsigned row_mask = 0; };
+    std::vector<V3Tables> tabs3;
     // sharding
     unsigned long long* d_flags = nullptr;
     double* peer_plane[kMaxWorld][3][2] = {};
@@ -366,6 +378,108 @@ static int32_t build_tables(Engine* e) {
     return QCA_OK;
 }
 
+// Window tables of the cluster kernels.  Pass 0: thread part = tile bits [0, 10-d) from the window x[0,10) << d,
+// row part = bits [10-d, 14+CB) from the window bits [10-2d, 14+CB+d).  Later pass with strided bits at H0 and
+// MT = 10-L of them on thread bits: thread part = the KA = max(0, MT-d) lowest strided bits (window
+// [H0-d, H0+KA+d): thread and tile-base bits only), row part = the rest including the cluster bits.
+static int32_t build_tables_v3(Engine* e) {
+    const int d = e->rule.distance;
+    const uint32_t imask = interval_mask_of(e->rule.act_lo, e->rule.act_hi);
+    e->tabs3.assign(e->passes3.size(), Engine::V3Tables{});
+    for (size_t i = 0; i < e->passes3.size(); ++i) {
+        const qca_pass_t& ps = e->passes3[i];
+        Engine::V3Tables& tb = e->tabs3[i];
+        const int cb = ps.reserved;
+        if (ps.high_bits == 0) {
+            QCA_CHECK(upload_table(e, window_table(kRowShift3 - d, d, imask), &tb.thr));
+            const int K = kRegHigh + d + cb;
+            QCA_CHECK(upload_table(e, window_table(K, d, imask), &tb.row));
+            tb.row_shift = kRowShift3 - 2 * d; tb.row_mask = (1u << (K + 2 * d)) - 1u; tb.row_pos = kRowShift3 - d;
+        } else {
+            const int L = ps.low_bits, H0 = ps.high_start, M = ps.high_bits;
+            const int MT = std::max(0, kRowShift3 - L);
+            const int KA = std::max(0, MT - d);
+            if (KA > 0) {
+                QCA_CHECK(upload_table(e, window_table(KA, d, imask), &tb.thr));
+                tb.thr_shift = H0 - d; tb.thr_mask = (1u << (KA + 2 * d)) - 1u; tb.thr_pos = L;
+            }
+            const int K = M + cb - KA;
+            QCA_CHECK(upload_table(e, window_table(K, d, imask), &tb.row));
+            tb.row_shift = H0 + KA - d; tb.row_mask = (1u << (K + 2 * d)) - 1u; tb.row_pos = L + KA;
+        }
+    }
+    return QCA_OK;
+}
+
+static int32_t launch_pass3(Engine* e, size_t pass_index, Pass3Args& a, int nunc) {
+    const qca_pass_t& ps = e->passes3[pass_index];
+    const Engine::V3Tables& tb = e->tabs3[pass_index];
+    const int cb = ps.reserved;
+    a.low_bits = ps.low_bits; a.high_start = ps.high_start; a.high_bits = ps.high_bits;
+    a.distance = e->rule.distance;
+    a.tab_thr = tb.thr; a.tab_row = tb.row;
+    a.thr_shift = tb.thr_shift; a.thr_pos = tb.thr_pos; a.thr_mask = tb.thr_mask;
+    a.row_shift = tb.row_shift; a.row_pos = tb.row_pos; a.row_mask = tb.row_mask;
+    a.ntiles = e->namps >> (kTile3 + cb);
+    for (unsigned r = 0; r < 16; ++r) {
+        const unsigned long long y = (unsigned long long)r << kRowShift3;
+        a.row_xg[r] = (y & ((1ull << ps.low_bits) - 1ull)) | ((y >> ps.low_bits) << ps.high_start);
+    }
+    const bool wide = (e->local_bits > 31);
+    Pass3Kernel kern = wide ? pass3_kernel_u64(ps.low_bits, nunc, cb) : pass3_kernel_u32(ps.low_bits, nunc, cb);
+    QCA_REQUIRE(kern != nullptr, QCA_ERR_UNSUPPORTED, "no cluster tile-pass kernel for %d low bits, %d operands, %d cluster bits",
+                ps.low_bits, nunc, cb);
+    if (std::find(e->configured.begin(), e->configured.end(), (const void*)kern) == e->configured.end()) {
+        QCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPass3SmemBytes));
+        e->configured.push_back((const void*)kern);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.ntiles << cb), e->nplanes, 1);
+    cfg.blockDim = dim3(kPass3Threads, 1, 1);
+    cfg.dynamicSmemBytes = kPass3SmemBytes;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1u << cb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cb ? 1 : 0;
+    const bool profile = (e->flags & QCA_FLAG_PROFILE) != 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (profile) {
+        QCA_CUDA(cudaEventCreate(&ev0)); QCA_CUDA(cudaEventCreate(&ev1));
+        QCA_CUDA(cudaEventRecord(ev0, e->stream));
+    }
+    QCA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    if (profile) {
+        QCA_CUDA(cudaEventRecord(ev1, e->stream));
+        e->prof.push_back({ev0, ev1, (int)pass_index});
+    }
+    e->st.pass_bytes += (2.0 + nunc) * (double)e->plane_bytes() * e->nplanes;   // in + out + local operands, once each
+    e->st.pass_launches += 1;
+    e->st.kernel_launches += 1;
+    return QCA_OK;
+}
+
+static int32_t apply_operator_v3(Engine* e, int v_out, int v_in, int v_a, double alpha, int v_c, double beta, double gamma) {
+    for (size_t i = 0; i < e->passes3.size(); ++i) {
+        Pass3Args a{};
+        int ns = 0;
+        auto add_local = [&](int v, double coef) {
+            for (int p = 0; p < 2; ++p) a.opnd[ns][p] = e->plane[v][p];
+            a.coef[ns++] = coef;
+        };
+        for (int p = 0; p < 2; ++p) { a.in[p] = e->plane[v_in][p]; a.out[p] = e->plane[v_out][p]; }
+        if (i == 0) {
+            if (v_a >= 0) add_local(v_a, alpha);
+            if (v_c >= 0) add_local(v_c, beta);
+        } else {
+            add_local(v_out, 1.0);
+        }
+        a.gamma = gamma;
+        QCA_CHECK(launch_pass3(e, i, a, ns));
+    }
+    return QCA_OK;
+}
+
 static int32_t launch_barrier(Engine* e) {
     if (e->world == 1 || e->loopback) return QCA_OK;
     QCA_REQUIRE(e->peers_ready, QCA_ERR_STATE, "sharded engine used before qca_exact_ipc_import");
@@ -453,6 +567,7 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
 // complete on every rank (barrier) because remote terms read the partner's copy of it.
 static int32_t apply_operator(Engine* e, int v_out, int v_in, int v_a, double alpha, int v_c, double beta,
                               double gamma) {
+    if (e->use_v3) return apply_operator_v3(e, v_out, v_in, v_a, alpha, v_c, beta, gamma);
     QCA_CHECK(launch_barrier(e));
     for (size_t i = 0; i < e->passes.size(); ++i) {
         PassArgs a{};
@@ -523,7 +638,7 @@ static int32_t ensure_work_planes(Engine* e) {
 // phi' = a_0 phi + (1/R) K B_1 + B_2.
 static int32_t step_once(Engine* e, double step_size) {
     const double t = (M_PI / 2.0) * step_size;
-    if (t == 0.0) return QCA_OK;
+    if (t == 0.0 || e->bound == 0.0) return QCA_OK;   // R == 0: no rule term can ever fire, H == 0 (e.g. a single cell)
     const double sgn = t < 0.0 ? -1.0 : 1.0;
     const double z = e->bound * fabs(t);
     std::vector<double> a;
@@ -567,7 +682,7 @@ constexpr int kGraphMaxBits = 24;
 
 static int32_t step_graphed(Engine* e, double step_size) {
     const bool eligible = e->world == 1 && e->local_bits > kSmallMaxBits && e->local_bits <= kGraphMaxBits &&
-                          !(e->flags & (QCA_FLAG_PROFILE | QCA_FLAG_NO_GRAPH)) && step_size != 0.0;
+                          !(e->flags & (QCA_FLAG_PROFILE | QCA_FLAG_NO_GRAPH)) && step_size != 0.0 && e->bound != 0.0;
     if (!eligible) return step_once(e, step_size);
     for (const Engine::StepGraph& g : e->graphs) {
         if (g.step_size == step_size && g.cur == e->cur && g.nplanes == e->nplanes && g.bound == e->bound) {
@@ -682,31 +797,41 @@ static unsigned stream_blocks(Engine* e, unsigned long long n) {
     return (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((n + 255) / 256, (unsigned long long)e->num_sms * 16));
 }
 
+// make the IO stream wait for everything queued on the compute stream so far
+static int32_t io_after_compute(Engine* e) {
+    QCA_CUDA(cudaEventRecord(e->io_event, e->stream));
+    QCA_CUDA(cudaStreamWaitEvent(e->io_stream, e->io_event, 0));
+    return QCA_OK;
+}
+
 static int32_t upload_vector(Engine* e, int v, const double* host, bool track) {
     QCA_CHECK(ensure_staging(e));
+    QCA_CHECK(io_after_compute(e));
     for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
         const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
-        QCA_CUDA(cudaMemcpyAsync(e->staging, host + 2 * off, cnt * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
-        unpack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
+        // (stream order on the IO stream protects the staging buffer: copy i+1 starts after unpack i)
+        QCA_CUDA(cudaMemcpyAsync(e->staging, host + 2 * off, cnt * sizeof(double2), cudaMemcpyHostToDevice, e->io_stream));
+        unpack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->io_stream>>>(
             e->staging, e->plane[v][0], e->plane[v][1], off, cnt, e->shard, e->d_maxabs + (track ? 0 : 2));
         QCA_CUDA(cudaGetLastError());
         e->st.kernel_launches += 1;
     }
+    QCA_CUDA(cudaStreamSynchronize(e->io_stream));   // the host buffer is the caller's again; later compute sees the planes
     return QCA_OK;
 }
 
 static int32_t download_vector(Engine* e, int v, double* host, int extra_quarter, bool both_planes) {
     QCA_CHECK(ensure_staging(e));
+    QCA_CHECK(io_after_compute(e));
     for (unsigned long long off = 0; off < e->namps; off += e->staging_amps) {
         const unsigned long long cnt = std::min(e->staging_amps, e->namps - off);
-        pack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->stream>>>(
+        pack_rotate_kernel<<<stream_blocks(e, cnt), 256, 0, e->io_stream>>>(
             e->staging, e->plane[v][0], both_planes ? e->plane[v][1] : nullptr, off, cnt, e->shard, extra_quarter);
         QCA_CUDA(cudaGetLastError());
         e->st.kernel_launches += 1;
-        QCA_CUDA(cudaMemcpyAsync(host + 2 * off, e->staging, cnt * sizeof(double2), cudaMemcpyDeviceToHost, e->stream));
-        // the staging buffer is reused by the next chunk
-        QCA_CUDA(cudaStreamSynchronize(e->stream));
+        QCA_CUDA(cudaMemcpyAsync(host + 2 * off, e->staging, cnt * sizeof(double2), cudaMemcpyDeviceToHost, e->io_stream));
     }
+    QCA_CUDA(cudaStreamSynchronize(e->io_stream));
     return QCA_OK;
 }
 
@@ -818,6 +943,7 @@ static int32_t block_norm(const qca_rule_t& rule, int nsites, unsigned long long
     int32_t rc = QCA_OK;
     do {
         e->fast_path = false;  // the generic kernel honours flip_mask
+        e->use_v3 = false;
         for (auto& ps : e->passes) ps.flip_mask &= centers;
         for (int v = 0; v < 3; ++v) if ((rc = ensure_plane(e, v, 0))) break;
         if (rc) break;
@@ -974,6 +1100,15 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
         }
         e->own_stream = true;
     }
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&e->io_stream, cudaStreamNonBlocking, greatest) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->io_event, cudaEventDisableTiming) != cudaSuccess) {
+            qca::set_error("creating the IO stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+            qca_exact_destroy(h); return QCA_ERR_CUDA;
+        }
+    }
     e->measure_blocks = e->num_sms * 8;
     bool ok = cudaMalloc(&e->d_maxabs, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&e->d_partials, std::max<size_t>(4ull * e->measure_blocks, (size_t)qca::kMeasureTileVals * 2 * e->num_sms) * sizeof(double)) == cudaSuccess &&
@@ -981,6 +1116,19 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
               cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
     if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
+    if (world_size == 1 && e->local_bits >= qca::kTile3 && rule->distance <= 4 && !(flags & QCA_FLAG_V2_KERNELS) && !getenv("QCA_V2_KERNELS")) {
+        // table of the per-row window: 4 + CB + 3 d index bits, kept at <= 16
+        int max_cb = std::min(qca::kMaxClusterBits, 16 - qca::kRegHigh - 3 * rule->distance);
+        if (const char* env = getenv("QCA_V3_CLUSTER_BITS")) max_cb = std::min(max_cb, std::max(0, atoi(env)));
+        int min_low = 4;
+        if (const char* env = getenv("QCA_V3_MIN_LOW")) min_low = atoi(env);
+        qca::plan_passes_v3(e->local_bits, std::max(0, max_cb), min_low, e->passes3);
+        e->use_v3 = !e->passes3.empty();
+        if (e->use_v3) {
+            if (int32_t rc = qca::build_tables_v3(e)) { qca_exact_destroy(h); return rc; }
+            e->st.passes_per_apply = (int32_t)e->passes3.size();
+        }
+    }
     if (!(flags & QCA_FLAG_LOOSE_BOUND)) {
         double tight = e->bound;
         if (int32_t rc = qca::tight_spectral_bound(*rule, device, &tight)) { qca_exact_destroy(h); return rc; }
@@ -1025,12 +1173,15 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->plane[v][p]) cudaFree(e->plane[v][p]);
     for (auto* p : e->d_tab_lo) if (p) cudaFree(p);
     for (auto* p : e->d_tab_hi) if (p) cudaFree(p);
+    for (auto& tb : e->tabs3) { if (tb.thr) cudaFree(tb.thr); if (tb.row) cudaFree(tb.row); }
     if (e->d_flags) cudaFree(e->d_flags);
     if (e->staging) cudaFree(e->staging);
     if (e->d_maxabs) cudaFree(e->d_maxabs);
     if (e->d_partials) cudaFree(e->d_partials);
     if (e->d_sums) cudaFree(e->d_sums);
     if (e->d_amp) cudaFree(e->d_amp);
+    if (e->io_stream) { cudaStreamSynchronize(e->io_stream); cudaStreamDestroy(e->io_stream); }
+    if (e->io_event) cudaEventDestroy(e->io_event);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete h;
     return QCA_OK;

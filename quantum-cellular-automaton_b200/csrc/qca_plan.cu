@@ -133,6 +133,41 @@ void plan_passes(int local_bits, std::vector<qca_pass_t>& out) {
     }
 }
 
+// Cluster plan (pass_kernel_v3, qca_pass3.cuh): CTA tiles of 14 bits, up to max_cluster_bits more through
+// distributed shared memory.  Pass 0 = the contiguous low bits (up to 17); every later pass takes up to
+// (14 - min_low) CTA-local strided bits plus up to max_cluster_bits cluster bits.  `reserved` of a pass holds its
+// number of cluster bits, high_bits the CTA-local strided bits only (the cluster bits follow directly above).
+// N = 30: 17 + 13 -> two passes (56 instead of 80 bytes per amplitude per Chebyshev term).
+void plan_passes_v3(int local_bits, int max_cluster_bits, int min_low, std::vector<qca_pass_t>& out) {
+    out.clear();
+    const int n = local_bits, T = 14;
+    if (n < T) return;
+    min_low = std::max(4, std::min(min_low, T - 1));
+    max_cluster_bits = std::max(0, std::min(max_cluster_bits, 3));
+    int covered = std::min(n, T + max_cluster_bits);
+    qca_pass_t p0{};
+    p0.low_bits = T; p0.high_start = T; p0.high_bits = 0; p0.reserved = covered - T;
+    p0.flip_mask = (1ull << covered) - 1ull;
+    out.push_back(p0);
+    int rem = n - covered;
+    if (rem <= 0) return;
+    const int local_max = T - min_low;
+    const int per = local_max + max_cluster_bits;
+    const int npass = (rem + per - 1) / per;
+    for (int i = 0; i < npass; ++i) {
+        const int m = rem / (npass - i) + ((rem % (npass - i)) ? 1 : 0);
+        const int cb = std::max(0, m - local_max);
+        qca_pass_t p{};
+        p.high_bits = m - cb;
+        p.low_bits = T - p.high_bits;
+        p.high_start = covered;
+        p.reserved = cb;
+        p.flip_mask = ((1ull << m) - 1ull) << covered;
+        out.push_back(p);
+        covered += m; rem -= m;
+    }
+}
+
 // Which qubits are sharded.  The partner-rank traffic of a sharded qubit's term is proportional to
 // how often its rule predicate holds on a rank, and for ADJACENT sharded cells that depends on the
 // rank itself (the rank whose top three cells are all alive pulls 2.75 planes per application, the
@@ -279,6 +314,20 @@ int32_t qca_plan_passes(int32_t local_bits, qca_pass_t* passes, int32_t capacity
     QCA_REQUIRE(npasses != nullptr, QCA_ERR_ARG, "npasses is NULL");
     std::vector<qca_pass_t> v;
     qca::plan_passes(local_bits, v);
+    *npasses = (int32_t)v.size();
+    if (passes != nullptr) {
+        QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "pass buffer too small");
+        memcpy(passes, v.data(), v.size() * sizeof(qca_pass_t));
+    }
+    return QCA_OK;
+}
+
+int32_t qca_plan_passes_v3(int32_t local_bits, int32_t max_cluster_bits, int32_t min_low, qca_pass_t* passes, int32_t capacity,
+                           int32_t* npasses) {
+    QCA_REQUIRE(local_bits >= 1 && local_bits <= 40, QCA_ERR_ARG, "local_bits out of range (%d)", local_bits);
+    QCA_REQUIRE(npasses != nullptr, QCA_ERR_ARG, "npasses is NULL");
+    std::vector<qca_pass_t> v;
+    qca::plan_passes_v3(local_bits, max_cluster_bits, min_low, v);
     *npasses = (int32_t)v.size();
     if (passes != nullptr) {
         QCA_REQUIRE(capacity >= (int32_t)v.size(), QCA_ERR_ARG, "pass buffer too small");

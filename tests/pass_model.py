@@ -258,3 +258,101 @@ def measure_tiles_model(vec: np.ndarray, ps: dict):
         g = t if t < L else H0 + (t - L)
         out.append((g, total - s1, s1, wt))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Model of the CLUSTER tile-pass kernel (csrc/qca_pass3.cuh): CTA tiles of 14 index bits, 2^CB CTAs per
+# cluster, predicates from one thread-constant and one per-row window-table lookup (build_tables_v3 in
+# csrc/qca_exact.cu).  Follows the kernel's index arithmetic statement by statement, vectorised over the
+# 512 threads x 16 rows of a CTA; `tile_bits` / `row_shift` are parameters so the CPU tests can also run
+# scaled-down geometries.
+# ---------------------------------------------------------------------------------------------
+def window_table(K: int, d: int, lo: int, hi: int) -> np.ndarray:
+    """entry[w] = activity of the middle K bits of the (K + 2d)-bit window w (qca_exact.cu window_table)."""
+    w = np.arange(1 << (K + 2 * d), dtype=np.int64)
+    return (activity(w, K + 2 * d, d, lo, hi) >> d) & ((1 << K) - 1)
+
+
+def v3_tables(ps: dict, d: int, lo: int, hi: int) -> dict:
+    """build_tables_v3 for one pass."""
+    ROWSHIFT, REGHIGH = 10, 4
+    cb = ps["cluster_bits"]
+    t = dict(thr=None, thr_shift=0, thr_pos=0, thr_mask=0)
+    if ps["high_bits"] == 0:
+        t["thr"] = window_table(ROWSHIFT - d, d, lo, hi)
+        K = REGHIGH + d + cb
+        t.update(row=window_table(K, d, lo, hi), row_shift=ROWSHIFT - 2 * d, row_mask=(1 << (K + 2 * d)) - 1, row_pos=ROWSHIFT - d)
+    else:
+        L, H0, M = ps["low_bits"], ps["high_start"], ps["high_bits"]
+        MT = max(0, ROWSHIFT - L)
+        KA = max(0, MT - d)
+        if KA > 0:
+            t.update(thr=window_table(KA, d, lo, hi), thr_shift=H0 - d, thr_mask=(1 << (KA + 2 * d)) - 1, thr_pos=L)
+        K = M + cb - KA
+        t.update(row=window_table(K, d, lo, hi), row_shift=H0 + KA - d, row_mask=(1 << (K + 2 * d)) - 1, row_pos=L + KA)
+    return t
+
+
+def apply_k_v3(vec: np.ndarray, passes: list, nbits: int, d: int, lo: int, hi: int) -> np.ndarray:
+    """K vec through the cluster kernel's arithmetic (one plane)."""
+    TILE, ROWSHIFT, THR = 14, 10, 9
+    out = np.zeros_like(vec)
+    tid = np.arange(512, dtype=np.int64)[None, :]
+    e = np.arange(16, dtype=np.int64)[:, None]
+    for ps in passes:
+        L, H0, M, CB = ps["low_bits"], ps["high_start"], ps["high_bits"], ps["cluster_bits"]
+        flip_low = M == 0
+        tb = v3_tables(ps, d, lo, hi)
+        low_mask = (1 << L) - 1
+        gap = H0 - L
+        ye = e << ROWSHIFT
+        row_xg = (ye & low_mask) | ((ye >> L) << H0)
+        for t in range(1 << (nbits - TILE - CB)):
+            t_lo, t_hi = t & ((1 << gap) - 1), t >> gap
+            staged = {}
+            xs_of = {}
+            for rank in range(1 << CB):
+                base = (t_lo << L) | (t_hi << (H0 + M + CB)) | (rank << (H0 + M))
+                y_thr = tid << 1
+                x_thr = base | (y_thr & low_mask) | ((y_thr >> L) << H0)
+                x = x_thr | row_xg                      # element 0 of the pair (row e, thread tid); element 1 = x | 1
+                xs_of[rank] = (x, x_thr)
+                staged[rank] = (vec[x], vec[x | 1])
+            for rank in range(1 << CB):
+                x, x_thr = xs_of[rank]
+                if flip_low:
+                    w = (x_thr & 0x3FF) << d
+                    thr0, thr1 = tb["thr"][w], tb["thr"][w | (1 << d)]
+                elif tb["thr"] is not None:
+                    thr0 = thr1 = tb["thr"][(x_thr >> tb["thr_shift"]) & tb["thr_mask"]] << tb["thr_pos"]
+                else:
+                    thr0 = thr1 = np.zeros_like(x_thr)
+                row_act = tb["row"][(x >> tb["row_shift"]) & tb["row_mask"]] << tb["row_pos"]
+                la0, la1 = thr0 | row_act, thr1 | row_act
+                v0, v1 = staged[rank]
+                acc0, acc1 = np.zeros(v0.shape), np.zeros(v0.shape)
+                qlo = 0 if flip_low else L
+                for k in range(CB):
+                    p0, p1 = staged[rank ^ (1 << k)]
+                    sg = -1.0 if (rank >> k) & 1 else 1.0
+                    on = ((la0 >> (TILE + k)) & 1).astype(bool)
+                    acc0 += np.where(on, sg * p0, 0.0)
+                    acc1 += np.where(on, sg * p1, 0.0)
+                if qlo == 0:
+                    acc0 += np.where(la0 & 1, v1, 0.0)
+                    acc1 -= np.where(la1 & 1, v0, 0.0)
+                for b in range(THR):
+                    if b + 1 >= qlo:
+                        partner = (tid ^ (1 << b))[0]
+                        sg = np.where((tid >> b) & 1, -1.0, 1.0)
+                        acc0 += np.where((la0 >> (b + 1)) & 1, sg * v0[:, partner], 0.0)
+                        acc1 += np.where((la1 >> (b + 1)) & 1, sg * v1[:, partner], 0.0)
+                for k in range(4):
+                    if ROWSHIFT + k >= qlo:
+                        prow = (e ^ (1 << k))[:, 0]
+                        sg = np.where((e >> k) & 1, -1.0, 1.0)
+                        acc0 += np.where((la0 >> (ROWSHIFT + k)) & 1, sg * v0[prow, :], 0.0)
+                        acc1 += np.where((la1 >> (ROWSHIFT + k)) & 1, sg * v1[prow, :], 0.0)
+                out[x] += acc0
+                out[x | 1] += acc1
+    return out

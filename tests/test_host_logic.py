@@ -230,3 +230,38 @@ def test_fused_measurement_decomposition(nbits):
         t = vec.reshape(-1, 2, 1 << g)
         assert abs(s0 - (t[:, 0, :] ** 2).sum()) < 1e-9 and abs(s1 - (t[:, 1, :] ** 2).sum()) < 1e-9
         assert abs(w - (t[:, 0, :] * t[:, 1, :]).sum()) < 1e-9
+
+
+@pytest.mark.parametrize("n,d,lo,hi,cbmax,minlow", [(14, 1, 1, 2, 3, 4), (15, 2, 2, 4, 3, 4), (17, 2, 2, 4, 3, 4), (18, 1, 1, 3, 3, 4),
+                                                   (19, 2, 2, 4, 1, 4), (18, 3, 2, 5, 3, 4), (19, 4, 3, 6, 0, 4), (20, 2, 2, 4, 2, 9),
+                                                   (19, 2, 1, 3, 0, 4)])
+def test_cluster_kernel_model_equals_rule_operator(n, d, lo, hi, cbmax, minlow):
+    """The cluster tile-pass kernel's arithmetic (tests/pass_model.apply_k_v3: plan from qca_plan_passes_v3, index
+    expansion, thread-constant + per-row window tables, partner-CTA exchange) reproduces K for every amplitude."""
+    passes = _lib.plan_passes_v3(n, cbmax, minlow)
+    covered = 0
+    for ps in passes:
+        assert ps["low_bits"] + ps["high_bits"] == 14 and ps["low_bits"] >= 4 and 0 <= ps["cluster_bits"] <= cbmax
+        assert covered & ps["flip_mask"] == 0
+        covered |= ps["flip_mask"]
+        m = ps["high_bits"] + ps["cluster_bits"]
+        want = ((1 << m) - 1) << ps["high_start"] if ps["high_bits"] else (1 << (14 + ps["cluster_bits"])) - 1
+        assert ps["flip_mask"] == want
+    assert covered == (1 << n) - 1
+    rng = np.random.default_rng(n)
+    phi = rng.standard_normal(1 << n)
+    got = pass_model.apply_k_v3(phi, passes, n, d, lo, hi)
+    xs = np.arange(1 << n, dtype=np.int64)
+    act = pass_model.activity(xs, n, d, lo, hi)
+    want = np.zeros_like(phi)
+    for g in range(n):
+        on = ((act >> g) & 1).astype(bool)
+        sign = np.where((xs >> g) & 1, -1.0, 1.0)
+        want[on] += sign[on] * phi[xs[on] ^ (1 << g)]
+    assert np.abs(got - want).max() < 1e-12
+
+
+def test_cluster_plan_of_the_benchmark_sizes():
+    assert [(p["low_bits"], p["high_bits"], p["cluster_bits"]) for p in _lib.plan_passes_v3(30)] == [(14, 0, 3), (4, 10, 3)]
+    assert [(p["low_bits"], p["high_bits"], p["cluster_bits"]) for p in _lib.plan_passes_v3(27)] == [(14, 0, 3), (4, 10, 0)]
+    assert len(_lib.plan_passes_v3(33)) == 3 and _lib.plan_passes_v3(13) == []
