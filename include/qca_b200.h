@@ -130,8 +130,8 @@ typedef struct qca_exact* qca_exact_t;
 #define QCA_FLAG_PROFILE 2u       /* record a CUDA-event pair around every kernel launch */
 #define QCA_FLAG_LOOSE_BOUND 4u   /* scale H by the Gershgorin bound only (skip the block-Lanczos bound) */
 #define QCA_FLAG_FUSED_MEASURE 8u   /* measure with one read of the state per tile pass (csrc/qca_measure.cu; single-plane
-                                       states on >= 13 local qubits) instead of one read per cell.  Default on one GPU;
-                                       sharded engines opt in with this flag or the environment variable QCA_FUSED_MEASURE */
+                                       states on >= 13 local qubits) instead of one read per cell.  The default (also when
+                                       sharded) */
 #define QCA_FLAG_TILE_PATH_ONLY 32u /* registers <= 13 qubits: use the tile-pass kernels instead of the one-kernel step (tests) */
 #define QCA_FLAG_NO_GRAPH 64u      /* registers of 14..24 qubits: launch a step kernel by kernel instead of replaying its CUDA graph */
 #define QCA_FLAG_V2_KERNELS 128u    /* one GPU, >= 14 qubits: use the 13-bit tile-pass kernels (pass_kernel_v2) instead of the

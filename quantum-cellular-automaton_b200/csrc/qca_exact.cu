@@ -1077,10 +1077,10 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     e->namps = 1ull << e->local_bits;
     qca::plan_shard(*rule, world_size, &e->shard, rank);
     e->flags = flags;
-    // fused measurement: default on one GPU (verified against the per-cell kernels), opt-in when sharded
-    if (getenv("QCA_FUSED_MEASURE") || (world_size == 1 && !getenv("QCA_PERCELL_MEASURE") && !(flags & QCA_FLAG_PERCELL_MEASURE)))
-        e->flags |= QCA_FLAG_FUSED_MEASURE;
-    if (flags & QCA_FLAG_PERCELL_MEASURE) e->flags &= ~QCA_FLAG_FUSED_MEASURE;
+    // fused measurement (one read of the state per tile pass): the default; sharded engines add the per-cell pairing of
+    // their slice with the partner's for the log2(P) sharded cells
+    if (!getenv("QCA_PERCELL_MEASURE") && !(flags & QCA_FLAG_PERCELL_MEASURE)) e->flags |= QCA_FLAG_FUSED_MEASURE;
+    else e->flags &= ~QCA_FLAG_FUSED_MEASURE;
     e->num_sms = prop.multiProcessorCount;
     e->bound = qca::spectral_bound(*rule);
     qca::plan_passes(e->local_bits, e->passes);

@@ -59,6 +59,8 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
     return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrival that publishes nothing (the end-of-tile "I have stopped reading your shared memory"): no fence
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned rank) {
     unsigned r;
@@ -67,8 +69,13 @@ __device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned ran
 }
 __device__ __forceinline__ double2 ld_dsmem(unsigned addr) {
     double2 v;
-    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
+}
+// v with its sign flipped when m == 0x80000000 (m is 0 otherwise): the (sigma^- - sigma^+) sign of a flip without a
+// register per thread bit (a table of +-1.0 doubles cost 18 registers of a 128-register budget)
+__device__ __forceinline__ double sign_flip(double v, unsigned m) {
+    return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
 }
 
 // L: contiguous low bits of the CTA tile, M = 14 - L strided bits at H0; CB cluster bits directly above them.
@@ -135,42 +142,42 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
     } else if (a.tab_thr) {
         thr_act0 = thr_act1 = (unsigned)a.tab_thr[(unsigned)((unsigned long long)x_thr >> a.thr_shift) & a.thr_mask] << a.thr_pos;
     }
-    double sgn[kThrBits3];
-#pragma unroll
-    for (int b = 0; b < kThrBits3; ++b) sgn[b] = ((tid >> b) & 1u) ? -1.0 : 1.0;
     // partner CTAs' tiles (same offset in their shared memory)
     unsigned peer[CB ? CB : 1];
-    double csgn[CB ? CB : 1];
     if (CB) {
         const unsigned mine = smem_u32(tile2 + tid);
 #pragma unroll
-        for (int k = 0; k < CB; ++k) {
-            peer[k] = map_to_rank(mine, rank ^ (1u << k));
-            csgn[k] = ((rank >> k) & 1u) ? -1.0 : 1.0;
-        }
+        for (int k = 0; k < CB; ++k) peer[k] = map_to_rank(mine, rank ^ (1u << k));
         cluster_arrive();   // my tile is staged ...
         cluster_wait();     // ... and so is everybody else's (also orders this CTA's own stores: no __syncthreads needed)
     } else {
         __syncthreads();
     }
+    // Row predicates and the partner CTAs' pairs are fetched ONE ROW AHEAD: a distributed-shared-memory load takes
+    // ~200+ cycles, and issued where it is consumed it was 45 % of the row time (ncu source page, round 2).
+    auto row_lookup = [&](int e) -> unsigned {
+        const unsigned long long xr = (unsigned long long)x_thr | a.row_xg[e];
+        return (unsigned)a.tab_row[(unsigned)(xr >> a.row_shift) & a.row_mask] << a.row_pos;
+    };
+    unsigned ract[2];
+    double2 rp[2][CB ? CB : 1];
+    auto fetch_remote = [&](int e, unsigned act, double2* dst) {   // (the predicate is uniform over the warp)
+#pragma unroll
+        for (int k = 0; k < CB; ++k)
+            if (act & (1u << (kTile3 + k))) dst[k] = ld_dsmem(peer[k] + (unsigned)(e << kThrBits3) * 16u);
+    };
+    ract[0] = row_lookup(0);
+    fetch_remote(0, ract[0], rp[0]);
 
 #pragma unroll
     for (int e = 0; e < kRows; ++e) {
-        const unsigned long long xr = (unsigned long long)x_thr | a.row_xg[e];
-        const unsigned row_act = (unsigned)a.tab_row[(unsigned)(xr >> a.row_shift) & a.row_mask] << a.row_pos;
+        if (e + 1 < kRows) {
+            ract[(e + 1) & 1] = row_lookup(e + 1);
+            fetch_remote(e + 1, ract[(e + 1) & 1], rp[(e + 1) & 1]);
+        }
+        const unsigned row_act = ract[e & 1];
         const unsigned la0 = thr_act0 | row_act, la1 = thr_act1 | row_act;
         double acc0 = 0.0, acc1 = 0.0;
-        // cluster bits first: the longest latency (the predicate is uniform over the warp)
-        if (CB) {
-#pragma unroll
-            for (int k = 0; k < CB; ++k) {
-                if (la0 & (1u << (kTile3 + k))) {
-                    const double2 p = ld_dsmem(peer[k] + (unsigned)(e << kThrBits3) * 16u);
-                    acc0 = fma(p.x, csgn[k], acc0);
-                    acc1 = fma(p.y, csgn[k], acc1);
-                }
-            }
-        }
         if (QLO == 0) {   // tile bit 0: the other half of the pair
             if (la0 & 1u) acc0 += v[e].y;
             if (la1 & 1u) acc1 -= v[e].x;
@@ -180,8 +187,9 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
         for (int b = 0; b < kThrBits3; ++b) {
             if (b + 1 >= QLO) {
                 const double2 p = tile2[(e << kThrBits3) | (tid ^ (1u << b))];
-                if (la0 & (2u << b)) acc0 = fma(p.x, sgn[b], acc0);
-                if (la1 & (2u << b)) acc1 = fma(p.y, sgn[b], acc1);
+                const unsigned m = (tid << (31 - b)) & 0x80000000u;
+                if (la0 & (2u << b)) acc0 += sign_flip(p.x, m);
+                if (la1 & (2u << b)) acc1 += sign_flip(p.y, m);
             }
         }
         // tile bits 10..13: partner row, same thread (registers)
@@ -195,6 +203,17 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
                 } else {
                     if (la0 & (1u << (kRowShift3 + k))) acc0 += p.x;
                     if (la1 & (1u << (kRowShift3 + k))) acc1 += p.y;
+                }
+            }
+        }
+        // cluster bits: the pairs fetched one row ago
+        if (CB) {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                if (row_act & (1u << (kTile3 + k))) {
+                    const unsigned m = (rank << (31 - k)) & 0x80000000u;
+                    acc0 += sign_flip(rp[e & 1][k].x, m);
+                    acc1 += sign_flip(rp[e & 1][k].y, m);
                 }
             }
         }
@@ -217,7 +236,7 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
         }
     }
     if (CB) {   // nobody may leave (and hand its shared memory to the next CTA) while a partner still reads its tile
-        cluster_arrive();
+        cluster_arrive_relaxed();
         cluster_wait();
     }
 }

@@ -3,7 +3,7 @@
 NVLink -- else the top cells; rank r holds the amplitudes whose sharded qubits spell r.
 
 ``torch.distributed`` is plumbing only: it moves the 64-byte CUDA-IPC handles once at start-up,
-two booleans after a state upload and the 4*N measurement sums per measure.  The data path (terms
+two booleans after a state upload and the 4*N measurement sums per measure (one all_gather of a tensor).  The data path (terms
 that flip a sharded qubit) is peer-memory loads inside the tile-pass kernel plus a device-side flag
 barrier (csrc/qca_exact.cu); no collective runs per step.
 """
@@ -37,6 +37,25 @@ def gather_objects(obj, group=None) -> list:
     out = [None] * world
     _dist().all_gather_object(out, obj, group=group)
     return out
+
+
+def gather_rows(vec: np.ndarray, device: int, group=None) -> np.ndarray:
+    """Every rank's float64 vector as the rows of one array, on every rank: ONE all_gather of a device tensor
+    (NCCL) or a host tensor (gloo) instead of a pickled all_gather_object (two collectives plus
+    serialisation; it was a measurable part of a sharded step at 8 GPUs)."""
+    world, _ = world_and_rank(group)
+    vec = np.ascontiguousarray(vec, dtype=np.float64)
+    if world == 1:
+        return vec[None, :]
+    import torch
+    dist = _dist()
+    on_gpu = dist.get_backend(group) == "nccl"
+    src = torch.from_numpy(vec)
+    if on_gpu:
+        src = src.to(torch.device("cuda", device))
+    out = torch.empty((world, vec.size), dtype=torch.float64, device=src.device)
+    dist.all_gather(list(out.unbind(0)), src, group=group)   # (supported by gloo and NCCL alike)
+    return out.cpu().numpy()
 
 
 def local_indices(nbits_total: int, positions: list[int], rank: int) -> np.ndarray:
@@ -80,6 +99,7 @@ class ShardedExactEngine:
         self.group = group
         self.world, self.rank = world_and_rank(group)
         self.ncells = int(rules.ncells)
+        self.device = device
         self._eng = _lib.ExactEngine(rules, device=device, world_size=self.world, rank=self.rank, flags=flags,
                                      stream=stream)
         self.local_amps = self._eng.local_amps
@@ -123,7 +143,7 @@ class ShardedExactEngine:
     def measure(self):
         if self.world == 1:
             return self._eng.measure()
-        return combine_measurements(gather_objects(self._eng.measure_partial(), self.group), self.ncells)
+        return combine_measurements(list(gather_rows(self._eng.measure_partial(), self.device, self.group)), self.ncells)
 
     def apply_h(self, vec) -> np.ndarray:
         arr = np.asarray(vec).reshape(-1)

@@ -179,6 +179,11 @@ def _gloo_worker(rank, world, port, n, ret):
         assert np.array_equal(sharding.assemble(slices, positions), psi)
         part = measure_partial_model(mine, n, nl, rank, world, slices, positions)
         pop, dpop, ent, bonds = sharding.combine_measurements(sharding.gather_objects(part), n)
+        # the product path gathers the sums as one tensor (gloo here, NCCL on the GPUs): same rows, same order
+        rows = sharding.gather_rows(np.asarray(part, dtype=np.float64), device=0)
+        assert rows.shape == (world, 4 * n) and np.array_equal(rows[rank], np.asarray(part, dtype=np.float64))
+        pop2, _, ent2, _ = sharding.combine_measurements(list(rows), n)
+        assert np.array_equal(pop2, pop) and np.array_equal(ent2, ent)
         pop_o, dpop_o, ent_o, bonds_o = oracle.measure_vector(psi, n)
         ok = (np.abs(pop - pop_o).max() < 1e-12 and np.abs(ent - ent_o).max() < 1e-11
               and np.array_equal(bonds, bonds_o) and np.array_equal(dpop, dpop_o))
