@@ -1117,9 +1117,14 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
     if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
     if (world_size == 1 && e->local_bits >= qca::kTile3 && rule->distance <= 4 && !(flags & QCA_FLAG_V2_KERNELS) && !getenv("QCA_V2_KERNELS")) {
-        // table of the per-row window: 4 + CB + 3 d index bits, kept at <= 16
-        int max_cb = std::min(qca::kMaxClusterBits, 16 - qca::kRegHigh - 3 * rule->distance);
-        if (const char* env = getenv("QCA_V3_CLUSTER_BITS")) max_cb = std::min(max_cb, std::max(0, atoi(env)));
+        // Cluster bits: OFF by default.  Measured on a B200 at N = 30 (profiles/r02_v3_cluster_sweep.txt): every cluster
+        // bit adds ~1.2 ms to a 6.5 ms pass -- distributed shared memory moves ~17 B/clk per SM, about what the SM's
+        // share of HBM moves, and the partner reads do not overlap the HBM stream -- so two passes with 3 + 3 cluster
+        // bits (21 ms per Chebyshev term) lose against three passes without (17 ms).  QCA_V3_CLUSTER_BITS=1..3 enables
+        // them (tests; future parts with faster SM-to-SM paths).  The per-row window table has 4 + CB + 3 d index bits.
+        int max_cb = 0;
+        if (const char* env = getenv("QCA_V3_CLUSTER_BITS"))
+            max_cb = std::max(0, std::min({atoi(env), qca::kMaxClusterBits, 16 - qca::kRegHigh - 3 * rule->distance}));
         int min_low = 4;
         if (const char* env = getenv("QCA_V3_MIN_LOW")) min_low = atoi(env);
         qca::plan_passes_v3(e->local_bits, std::max(0, max_cb), min_low, e->passes3);

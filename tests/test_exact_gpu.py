@@ -97,7 +97,7 @@ def test_fast_kernel_step_and_measure_vs_c_oracle(n, d, lo, hi, state, tau):
         assert np.abs(pop - pop_o).max() < TOL and np.abs(ent - ent_o).max() < TOL, (k, n)
         eng.step(tau, 1)
         ref.step(tau)
-    assert eng.stats()["passes_per_apply"] == len(_lib.plan_passes_v3(n) or _lib.plan_passes(n))
+    assert eng.stats()["passes_per_apply"] == len(_lib.plan_passes_v3(n, 0) or _lib.plan_passes(n))
     assert np.abs(eng.get_state() - ref.psi).max() < 1e-11
     eng.close()
 
@@ -247,7 +247,7 @@ def test_zero_step_is_identity_and_stats_count_launches():
     eng.reset_stats()
     eng.step(1.0, 1)
     st = eng.stats()
-    assert st["passes_per_apply"] == len(_lib.plan_passes_v3(15)) and st["last_terms"] > 10
+    assert st["passes_per_apply"] == len(_lib.plan_passes_v3(15, 0)) and st["last_terms"] > 10
     assert st["pass_launches"] == (st["last_terms"] - 1) * st["passes_per_apply"]
     assert st["profiled_pass_launches"] == st["pass_launches"] and st["profiled_pass_ms"] > 0.0
 
@@ -391,10 +391,11 @@ def test_graph_replay_equals_eager_launches(n, d, lo, hi, state):
 
 
 @pytest.mark.parametrize("n,d,lo,hi,env", [
-    (14, 1, 1, 2, {}), (15, 2, 2, 4, {}), (16, 2, 1, 3, {}), (17, 2, 2, 4, {}), (18, 1, 1, 3, {}), (20, 3, 2, 5, {}),
-    (21, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "0"}), (21, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "1"}),
+    (14, 1, 1, 2, {}), (15, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "3"}), (16, 2, 1, 3, {"QCA_V3_CLUSTER_BITS": "3"}),
+    (17, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "3"}), (18, 1, 1, 3, {"QCA_V3_CLUSTER_BITS": "3"}), (20, 3, 2, 5, {"QCA_V3_CLUSTER_BITS": "3"}),
+    (21, 2, 2, 4, {}), (21, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "1"}), (19, 3, 2, 5, {}),
     (22, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "2"}), (22, 1, 1, 2, {"QCA_V3_MIN_LOW": "10"}), (23, 4, 3, 6, {}),
-    (24, 2, 2, 4, {"QCA_V3_MIN_LOW": "7"}), (25, 2, 2, 4, {})])
+    (24, 2, 2, 4, {"QCA_V3_MIN_LOW": "7", "QCA_V3_CLUSTER_BITS": "3"}), (25, 2, 2, 4, {"QCA_V3_CLUSTER_BITS": "3"}), (26, 2, 2, 4, {})])
 def test_cluster_kernels_equal_13_bit_kernels(n, d, lo, hi, env, monkeypatch):
     """pass_kernel_v3 (14-bit CTA tiles joined through distributed shared memory, the default on one GPU from 14
     qubits) against pass_kernel_v2 (QCA_FLAG_V2_KERNELS) on the same inputs: H psi on a seeded complex vector, and two
@@ -405,7 +406,7 @@ def test_cluster_kernels_equal_13_bit_kernels(n, d, lo, hi, env, monkeypatch):
     rules = qca_b200.Rules(n, range(lo, hi), d)
     v3 = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_LOOSE_BOUND)
     v2 = _lib.ExactEngine(rules, flags=_lib.QCA_FLAG_LOOSE_BOUND | _lib.QCA_FLAG_V2_KERNELS)
-    cb = int(env.get("QCA_V3_CLUSTER_BITS", 3)) if d <= 3 else 0
+    cb = int(env.get("QCA_V3_CLUSTER_BITS", 0)) if d <= 3 else 0
     assert v3.stats()["passes_per_apply"] == len(_lib.plan_passes_v3(n, cb, int(env.get("QCA_V3_MIN_LOW", 4))))
     assert v2.stats()["passes_per_apply"] == len(_lib.plan_passes(n))
     rng = np.random.default_rng(n)
