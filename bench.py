@@ -279,7 +279,7 @@ def b200_arm(args) -> None:
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL prints its version banner on STDOUT otherwise
+        # (NCCL_DEBUG stays unset: at VERSION or above NCCL prints its version banner on STDOUT, next to the JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a real (non-default) stream: handle 0 would make the library create its own stream and the
     # torch events below would not see the kernels
