@@ -136,6 +136,9 @@ typedef struct qca_exact* qca_exact_t;
 #define QCA_FLAG_NO_GRAPH 64u      /* registers of 14..24 qubits: launch a step kernel by kernel instead of replaying its CUDA graph */
 #define QCA_FLAG_V2_KERNELS 128u    /* one GPU, >= 14 qubits: use the 13-bit tile-pass kernels (pass_kernel_v2) instead of the
                                       cluster kernels (pass_kernel_v3); also: environment QCA_V2_KERNELS */
+#define QCA_FLAG_NO_PERSISTENT 256u /* sharded engines: one CTA per tile (pass_kernel_v2) instead of persistent CTAs whose operand
+                                      rings run across tile boundaries (pass_kernel_v2p); environment QCA_PERSISTENT_CTAS=0 likewise,
+                                      QCA_PERSISTENT_CTAS=n > 0 limits the persistent grid to n CTAs (tests) */
 #define QCA_FLAG_PERCELL_MEASURE 16u /* always use the per-cell measurement kernels (also: environment QCA_PERCELL_MEASURE) */
 
 /* Exact.__init__ (exact.py:15-17).  Instead of MPO.as_matrix() + calculate_U

@@ -35,6 +35,7 @@ QCA_FLAG_PERCELL_MEASURE = 16
 QCA_FLAG_TILE_PATH_ONLY = 32
 QCA_FLAG_NO_GRAPH = 64
 QCA_FLAG_V2_KERNELS = 128
+QCA_FLAG_NO_PERSISTENT = 256
 QCA_IPC_HANDLE_BYTES = 64
 
 

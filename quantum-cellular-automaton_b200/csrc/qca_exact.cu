@@ -240,6 +240,7 @@ struct Engine {
     std::vector<qca_pass_t> passes;
     std::vector<qca_remote_op_t> remote;
     qca_remote_rotation_t rotation{};  // fast kernel: how the remote terms rotate over the passes
+    int persistent_ctas = -1;          // sharded fast kernel: -1 persistent with 2 CTAs per SM, 0 one CTA per tile (pass_kernel_v2), > 0 that many CTAs
     int remote_rows = 6;               // rows of the remote operand ring (QCA_REMOTE_RING=4: shallower, deeper local ring)
     double remote_fraction[64] = {};   // per sharded qubit (global bit): fraction of the plane its term reads
     double2* staging = nullptr;
@@ -522,6 +523,14 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
     if (e->fast_path && T == kTile && nunc == a.nstreams)   // remote terms travel in a.rs
         kern = wide ? fast_pass_kernel_u64(ps.low_bits, nunc, a.nrem, e->remote_rows)
                     : fast_pass_kernel_u32(ps.low_bits, nunc, a.nrem, e->remote_rows);
+    // sharded launches: persistent CTAs whose operand rings run across tile boundaries (pass_kernel_v2p)
+    bool persistent = false;
+    if (kern != nullptr && a.nrem > 0 && e->persistent_ctas != 0) {
+        const int rd = (e->remote_rows == 4) ? 4 : 8;
+        PassKernel pk = wide ? persistent_pass_kernel_u64(ps.low_bits, nunc, a.nrem, rd)
+                             : persistent_pass_kernel_u32(ps.low_bits, nunc, a.nrem, rd);
+        if (pk != nullptr) { kern = pk; persistent = true; }
+    }
     const bool fast = kern != nullptr;
     if (fast) smem = kPassSmemBytes;
     else {
@@ -535,6 +544,9 @@ static int32_t launch_pass(Engine* e, size_t pass_index, PassArgs& a) {
         e->configured.push_back((const void*)kern);
     }
     unsigned gx = (unsigned)std::min<unsigned long long>(a.ntiles, 1u << 30);
+    if (persistent)   // two resident CTAs per SM (QCA_PERSISTENT_CTAS: tests walk many tiles per CTA on small registers)
+        gx = (unsigned)std::min<unsigned long long>(a.ntiles, e->persistent_ctas > 0 ? (unsigned long long)e->persistent_ctas
+                                                                                        : 2ull * e->num_sms / std::max(e->nplanes, 1));
     dim3 grid(gx, e->nplanes, 1);
     const bool profile = (e->flags & QCA_FLAG_PROFILE) != 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1070,6 +1082,11 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     QCA_REQUIRE(prop.major >= 10, QCA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
                 device, prop.major, prop.minor);
 
+    const bool dbg = getenv("QCA_DEBUG") != nullptr;
+    auto peek = [&](const char* where) {
+        if (dbg) fprintf(stderr, "qca_b200 debug: %s: %s\n", where, cudaGetErrorString(cudaPeekAtLastError()));
+    };
+    peek("create entry");
     qca_exact* h = new qca_exact();
     Engine* e = &h->e;
     e->rule = *rule; e->device = device; e->world = world_size; e->rank = rank; e->rank_bits = rank_bits;
@@ -1087,6 +1104,8 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
     if (int32_t rc = qca::plan_remote(*rule, world_size, rank, e->remote)) { delete h; return rc; }
     if (int32_t rc = qca::plan_rotation(*rule, world_size, rank, &e->rotation)) { delete h; return rc; }
     if (const char* env = getenv("QCA_REMOTE_RING")) e->remote_rows = (atoi(env) == 4) ? 4 : 6;
+    if (flags & QCA_FLAG_NO_PERSISTENT) e->persistent_ctas = 0;
+    else if (const char* env = getenv("QCA_PERSISTENT_CTAS")) e->persistent_ctas = atoi(env);
     for (const qca_remote_op_t& op : e->remote)  // fraction of the plane the term reads on this rank
         e->remote_fraction[op.qubit] = op.window_bits <= 4
             ? (double)__builtin_popcount(op.mask & 0xffffu) / 16.0 : 1.0;   // the mask is replicated over 16 entries
@@ -1115,7 +1134,9 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
               cudaMalloc(&e->d_sums, 4ull * rule->ncells * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&e->d_amp, 2ull * rule->ncells * sizeof(double)) == cudaSuccess;
     if (!ok) { qca::set_error("cudaMalloc of scratch failed: %s", cudaGetErrorString(cudaGetLastError())); qca_exact_destroy(h); return QCA_ERR_NOMEM; }
+    peek("before tables");
     if (int32_t rc = qca::build_tables(e)) { qca_exact_destroy(h); return rc; }
+    peek("after tables");
     if (world_size == 1 && e->local_bits >= qca::kTile3 && rule->distance <= 4 && !(flags & QCA_FLAG_V2_KERNELS) && !getenv("QCA_V2_KERNELS")) {
         // Cluster bits: OFF by default.  Measured on a B200 at N = 30 (profiles/r02_v3_cluster_sweep.txt): every cluster
         // bit adds ~1.2 ms to a 6.5 ms pass -- distributed shared memory moves ~17 B/clk per SM, about what the SM's
@@ -1134,6 +1155,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
             e->st.passes_per_apply = (int32_t)e->passes3.size();
         }
     }
+    peek("before bound");
     if (!(flags & QCA_FLAG_LOOSE_BOUND)) {
         double tight = e->bound;
         if (int32_t rc = qca::tight_spectral_bound(*rule, device, &tight)) { qca_exact_destroy(h); return rc; }
@@ -1144,6 +1166,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
         if (tight < e->bound) e->bound = tight;
         e->st.spectral_bound = e->bound;
     }
+    peek("after bound");
     if (world_size > 1) {
         // every plane exists up front so that it can be exported once
         for (int v = 0; v < 3; ++v)
@@ -1157,6 +1180,7 @@ int32_t qca_exact_create(qca_exact_t* out, const qca_rule_t* rule, int32_t devic
         }
         e->peer_flags[rank] = e->d_flags;
     }
+    peek("create exit");
     *out = h;
     return QCA_OK;
 }
@@ -1168,7 +1192,7 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& pr : e->prof) { cudaEventDestroy(pr.ev0); cudaEventDestroy(pr.ev1); }
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
-    if (e->peers_ready) {
+    if (e->peers_ready && !e->loopback) {   // (loop-back "peers" are this engine's own planes, not IPC mappings)
         for (int r = 0; r < e->world; ++r) {
             if (r == e->rank) continue;
             for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->peer_plane[r][v][p]) cudaIpcCloseMemHandle(e->peer_plane[r][v][p]);
@@ -1188,6 +1212,7 @@ int32_t qca_exact_destroy(qca_exact_t h) {
     if (e->io_stream) { cudaStreamSynchronize(e->io_stream); cudaStreamDestroy(e->io_stream); }
     if (e->io_event) cudaEventDestroy(e->io_event);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    cudaGetLastError();   // nothing a teardown call reported may surface in a later engine's launch check
     delete h;
     return QCA_OK;
 }

@@ -451,10 +451,254 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fast kernel, sharded registers, PERSISTENT variant.
+//
+// pass_kernel_v2 gives every tile its own CTA: the partner rows of a tile are requested at CTA entry and the
+// first of them is needed 2-3 us later, sooner than NVLink answers, so every tile starts with a stall (about a
+// quarter of the sharded launch at 8 GPUs).  Here a CTA walks over tiles t, t + gridDim.x, ... and its
+// operand rings run on across the tile boundary: while the last DC (DU) rows of a tile are processed, the first
+// rows of the NEXT tile are already being fetched -- remote rows by bulk copies over NVLink, local rows by
+// cp.async -- so in steady state a remote row has DC row times (5-6 us) to arrive.  Ring depths divide 16 so the
+// slot of a row is the same in every tile; the phase of an mbarrier is the parity of the active uses of its slot
+// so far: the uses inside the tile (a popcount against a compile-time mask) plus a carried bit per slot.
+// ---------------------------------------------------------------------------
+template <typename I, int L, bool FLIP_LOW, int NUNC, int NREM, int DC>
+__global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2p(const PassArgs a) {
+    constexpr int M = kTile - L;
+    constexpr int QLO = FLIP_LOW ? 0 : L;
+    constexpr int DU_FREE = NUNC == 0 ? 0 : (ring_rows(NREM) - NREM * DC) / (NUNC ? NUNC : 1);
+    constexpr int DU = DU_FREE >= 8 ? 8 : (DU_FREE >= 4 ? 4 : (DU_FREE >= 2 ? 2 : (DU_FREE >= 1 ? 1 : 0)));
+    constexpr int CHUNK_LANES = (L >= 6) ? 32 : (1 << (L - 1));
+    constexpr int ISSUERS = 32 / CHUNK_LANES;
+    static_assert(NREM >= 1 && NREM <= kMaxRemoteSlots && (DC == 4 || DC == 8), "remote ring");
+    static_assert(NUNC == 0 || DU >= 1, "local ring");
+    static_assert(NUNC * DU + NREM * DC <= ring_rows(NREM), "ring budget");
+    static_assert(ISSUERS * NREM * DC <= 32, "mbarrier budget: 32 per warp");
+    static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
+    static_assert(L >= 4, "rows of at least 128 bytes");
+    extern __shared__ double tile[];
+    const int plane = blockIdx.y;
+    const double* __restrict__ in = a.in[plane];
+    double* out = a.out[plane];
+    const int H0 = a.high_start;
+    const int d = a.distance;
+    const unsigned tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    constexpr unsigned low_mask = (1u << L) - 1u;
+    const int gap = H0 - L;
+    const unsigned y_thr = tid << 1;
+
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+    double2* ring = tile2 + (1 << (kTile - 1));
+    double2* rring = ring + NUNC * DU * kPassThreads;
+    const unsigned mbar0 = smem_u32(ring + (kRingRowsTotal - 1) * kPassThreads) + warp * 256u;
+    constexpr int NBAR = NREM * DC;
+    const unsigned piece = lane / CHUNK_LANES;
+
+    // everything that depends on the tile
+    struct TileCtx { I x_thr; unsigned act[NREM]; unsigned rot0, rot1; };
+    auto setup = [&](unsigned long long t, TileCtx& c) {
+        const I t_lo = (I)(t & ((1ull << gap) - 1ull));
+        const I t_hi = (I)(t >> gap);
+        const I base = (t_lo << L) | (t_hi << (H0 + M));
+        c.x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
+        c.rot0 = c.rot1 = 0;
+#pragma unroll
+        for (int k = 0; k < NREM; ++k) c.act[k] = 0;
+        constexpr int ROWS_PER_LANE = (CHUNK_LANES >= 16) ? 1 : 16 / CHUNK_LANES;
+        constexpr int FIELD = (CHUNK_LANES >= 16) ? 16 : CHUNK_LANES;
+        const unsigned field_shift = (CHUNK_LANES >= 32) ? 0u : piece * CHUNK_LANES;
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_LANE; ++q) {
+            const unsigned e = ((lane & (CHUNK_LANES - 1)) + q * CHUNK_LANES) & 15u;
+            const unsigned ye = e << kRowShift;
+            const I x = c.x_thr | (I)(ye & low_mask) | ((I)(ye >> L) << H0);
+            const unsigned rot = (a.rot_word >> (2u * ((unsigned)(x >> a.rot_shift) & 15u))) & 3u;
+            const unsigned v0 = __ballot_sync(0xffffffffu, rot & 1u), v1 = __ballot_sync(0xffffffffu, rot & 2u);
+            c.rot0 |= ((v0 >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+            c.rot1 |= ((v1 >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+#pragma unroll
+            for (int k = 0; k < NREM; ++k) {
+                const RemoteAlt* al = &a.rs[k].alt[rot];
+                const unsigned vk = __ballot_sync(0xffffffffu, (al->mask >> ((unsigned)(x >> al->shift) & 15u)) & 1u);
+                c.act[k] |= ((vk >> field_shift) & ((1u << FIELD) - 1u)) << (q * FIELD);
+            }
+        }
+    };
+    auto row_off = [&](int e) -> I {   // index bits of register row e (compile-time after unrolling)
+        const unsigned ye = (unsigned)e << kRowShift;
+        return (I)(ye & low_mask) | ((I)(ye >> L) << H0);
+    };
+    auto local_slot = [&](int k, int e) -> double2* { return ring + ((k * DU + (e % (DU ? DU : 1))) * kPassThreads + tid); };
+    auto remote_slot = [&](int k, int e) -> double2* { return rring + ((k * DC + (e % DC)) * kPassThreads + tid); };
+    auto remote_bar = [&](int k, int e) -> unsigned { return mbar0 + (piece * NBAR + (unsigned)(k * DC + (e % DC))) * 8u; };
+    auto uses_before = [](int e) -> unsigned {   // rows e' < e of the same tile in the same ring slot
+        unsigned m = 0;
+        for (int q = e % DC; q < e; q += DC) m |= 1u << q;
+        return m;
+    };
+    auto slot_class = [](int s) -> unsigned {    // all rows of a tile that use ring slot s
+        unsigned m = 0;
+        for (int q = s; q < kRows; q += DC) m |= 1u << q;
+        return m;
+    };
+    auto remote_issue = [&](const TileCtx& c, int e) {
+#pragma unroll
+        for (int k = 0; k < NREM; ++k) {
+            if (((c.act[k] >> e) & 1u) && (lane & (CHUNK_LANES - 1)) == 0) {
+                const unsigned rot = ((c.rot0 >> e) & 1u) | (((c.rot1 >> e) & 1u) << 1);
+                const RemoteAlt* al = &a.rs[k].alt[rot];
+                const unsigned bar = remote_bar(k, e);
+                mbar_arrive_expect_tx(bar, CHUNK_LANES * 16);
+                bulk_g2s(smem_u32(remote_slot(k, e)), al->ptr[plane] + (c.x_thr | row_off(e)), CHUNK_LANES * 16, bar);
+            }
+        }
+    };
+    auto local_fetch = [&](const TileCtx& c, int e) {
+#pragma unroll
+        for (int k = 0; k < NUNC; ++k) cp_async16(local_slot(k, e), a.s[k].ptr[plane] + (c.x_thr | row_off(e)));
+    };
+
+    unsigned long long t = blockIdx.x;
+    if (t >= a.ntiles) return;
+    TileCtx cur, nxt;
+    setup(t, cur);
+    unsigned carry[NREM];   // bit s: parity of the active uses of ring slot s in the tiles done so far
+#pragma unroll
+    for (int k = 0; k < NREM; ++k) carry[k] = 0;
+    // ---- prologue: barriers, first rows of the first tile ----------------------------------------------
+    if (lane < ISSUERS * NBAR) mbar_init(mbar0 + lane * 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < DC; ++e) remote_issue(cur, e);
+    if (NUNC) {
+#pragma unroll
+        for (int e = 0; e < DU; ++e) {
+            local_fetch(cur, e);
+            cp_async_commit();
+        }
+    }
+    double sgn[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) sgn[b] = ((tid >> b) & 1u) ? -1.0 : 1.0;
+
+    for (;;) {
+        const unsigned long long t_next = t + gridDim.x;
+        const bool has_next = t_next < a.ntiles;   // uniform over the CTA
+        if (has_next) setup(t_next, nxt);
+        // ---- stage the tile ------------------------------------------------------------------------
+        double2 v[kRows];
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + (cur.x_thr | row_off(e)));
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
+        unsigned lo_act0 = 0, lo_act1 = 0;
+        if (FLIP_LOW) {
+            const unsigned w = ((unsigned)cur.x_thr & 0x1ffu) << d;
+            lo_act0 = a.tab_lo[w];
+            lo_act1 = a.tab_lo[w | (1u << d)];
+        }
+        const unsigned long long xg_thr = expand_index((unsigned long long)cur.x_thr, a.shard);
+        __syncthreads();
+
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) {
+            unsigned la0, la1;
+            const unsigned long long xg = xg_thr | a.row_xg[e];
+            if (FLIP_LOW) {
+                const int S = 9 - d;
+                const unsigned w = (unsigned)(xg >> (9 - 2 * d)) & ((1u << (4 + 3 * d)) - 1u);
+                const unsigned hi_act = a.tab_hi[w];
+                la0 = lo_act0 | (hi_act << S);
+                la1 = lo_act1 | (hi_act << S);
+            } else {
+                const unsigned w = (unsigned)(xg >> a.win_shift) & a.win_mask;
+                la0 = la1 = (unsigned)a.tab_hi[w] << L;
+            }
+            double acc0 = 0.0, acc1 = 0.0;
+            if (QLO == 0) {
+                if (la0 & 1u) acc0 += v[e].y;
+                if (la1 & 1u) acc1 -= v[e].x;
+            }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b + 1 >= QLO) {
+                    const double2 p = tile2[(e << (kRowShift - 1)) | (tid ^ (1u << b))];
+                    if (la0 & (2u << b)) acc0 = fma(p.x, sgn[b], acc0);
+                    if (la1 & (2u << b)) acc1 = fma(p.y, sgn[b], acc1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kRegHigh; ++k) {
+                if (kRowShift + k >= QLO) {
+                    const double2 p = v[e ^ (1 << k)];
+                    if ((e >> k) & 1) {
+                        if (la0 & (1u << (kRowShift + k))) acc0 -= p.x;
+                        if (la1 & (1u << (kRowShift + k))) acc1 -= p.y;
+                    } else {
+                        if (la0 & (1u << (kRowShift + k))) acc0 += p.x;
+                        if (la1 & (1u << (kRowShift + k))) acc1 += p.y;
+                    }
+                }
+            }
+            double2 r;
+            r.x = a.gamma * acc0;
+            r.y = a.gamma * acc1;
+            if (NUNC) {
+                cp_async_wait<(NUNC ? DU : 1) - 1>();   // one commit group per row, in every tile: row e has landed
+#pragma unroll
+                for (int k = 0; k < NUNC; ++k) {
+                    const double2 sv = *local_slot(k, e);
+                    r.x = fma(a.s[k].coef, sv.x, r.x);
+                    r.y = fma(a.s[k].coef, sv.y, r.y);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NREM; ++k) {
+                if ((cur.act[k] >> e) & 1u) {
+                    const unsigned parity = (__popc(cur.act[k] & uses_before(e)) + ((carry[k] >> (e % DC)) & 1u)) & 1u;
+                    mbar_wait(remote_bar(k, e), parity);
+                    const double2 sv = *remote_slot(k, e);
+                    const unsigned rot = ((cur.rot0 >> e) & 1u) | (((cur.rot1 >> e) & 1u) << 1);
+                    const double coef = a.rs[k].alt[rot].coef;
+                    r.x = fma(coef, sv.x, r.x);
+                    r.y = fma(coef, sv.y, r.y);
+                }
+            }
+            stg_stream(out + (cur.x_thr | row_off(e)), r);
+            // refill the slots just consumed: later rows of this tile, then the first rows of the next one
+            if (NUNC) {
+                if (e + DU < kRows) local_fetch(cur, e + DU);
+                else if (has_next) local_fetch(nxt, e + DU - kRows);
+                cp_async_commit();
+            }
+            __syncwarp();   // every lane has read row e of the remote ring: its slots may be overwritten
+            if (e + DC < kRows) remote_issue(cur, e + DC);
+            else if (has_next) remote_issue(nxt, e + DC - kRows);
+        }
+        if (!has_next) break;
+#pragma unroll
+        for (int k = 0; k < NREM; ++k) {
+            unsigned flip = 0;
+#pragma unroll
+            for (int s = 0; s < DC; ++s) flip |= (unsigned)(__popc(cur.act[k] & slot_class(s)) & 1) << s;
+            carry[k] ^= flip;
+        }
+        t = t_next;
+        cur = nxt;
+        __syncthreads();   // everybody has read the staged tile: the next one may overwrite it
+    }
+}
+
 // kernel tables, one translation unit per index type (qca_pass_u32.cu / qca_pass_u64.cu)
 typedef void (*PassKernel)(const PassArgs);
 PassKernel fast_pass_kernel_u32(int low_bits, int nunc, int nrem, int remote_rows);
 PassKernel fast_pass_kernel_u64(int low_bits, int nunc, int nrem, int remote_rows);
+PassKernel persistent_pass_kernel_u32(int low_bits, int nunc, int nrem, int remote_rows);
+PassKernel persistent_pass_kernel_u64(int low_bits, int nunc, int nrem, int remote_rows);
 PassKernel generic_pass_kernel(bool wide);
 
 }  // namespace qca

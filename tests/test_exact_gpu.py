@@ -424,3 +424,41 @@ def test_cluster_kernels_equal_13_bit_kernels(n, d, lo, hi, env, monkeypatch):
     if n <= 22:
         assert np.abs(v3.get_state() - v2.get_state()).max() < 1e-12
     v3.close(), v2.close()
+
+
+@pytest.mark.parametrize("n,world,rank,d,lo,hi,env", [
+    (17, 2, 1, 2, 2, 4, {"QCA_PERSISTENT_CTAS": "3"}), (18, 2, 0, 1, 1, 2, {"QCA_PERSISTENT_CTAS": "5", "QCA_FORCE_SLOTS2": "1"}),
+    (19, 4, 2, 2, 2, 4, {"QCA_PERSISTENT_CTAS": "7"}), (20, 4, 3, 2, 1, 3, {"QCA_PERSISTENT_CTAS": "2", "QCA_REMOTE_RING": "4"}),
+    (21, 8, 5, 2, 2, 4, {"QCA_PERSISTENT_CTAS": "3"}), (22, 8, 0, 2, 2, 4, {"QCA_PERSISTENT_CTAS": "11"}),
+    (20, 8, 7, 1, 1, 2, {"QCA_PERSISTENT_CTAS": "1"}), (24, 8, 6, 2, 2, 4, {}), (23, 2, 1, 2, 2, 4, {})])
+def test_persistent_sharded_kernel_equals_one_cta_per_tile(n, world, rank, d, lo, hi, env, monkeypatch):
+    """pass_kernel_v2p (persistent CTAs, operand rings running across tile boundaries, carried mbarrier phases) against
+    pass_kernel_v2 (one CTA per tile) on ONE GPU: a sharded engine whose partners are looped back to its own planes
+    (qca_exact_loopback_peers).  The physics of such an engine is meaningless, the arithmetic is not: both kernels must
+    produce bit-identical vectors, for every rank/world geometry, with few CTAs walking many tiles each."""
+    rules = qca_b200.Rules(n, range(lo, hi), d)
+    plist = list(np.random.default_rng(100 + n).uniform(0.1, 0.9, n))   # every rank's slice is populated, one real plane
+    results = []
+    for persistent in (True, False):
+        for k, v in env.items():
+            if persistent or k != "QCA_PERSISTENT_CTAS":
+                monkeypatch.setenv(k, v)
+        flags = _lib.QCA_FLAG_LOOSE_BOUND | (0 if persistent else _lib.QCA_FLAG_NO_PERSISTENT)
+        eng = _lib.ExactEngine(rules, world_size=world, rank=rank, flags=flags)
+        eng.loopback_peers()
+        eng.set_product_state(plist)
+        eng.resolve_planes(*eng.plane_flags())
+        eng.step(1.0, 2)
+        rng = np.random.default_rng(n)
+        results.append((eng.get_state(), eng.measure_partial(), eng.stats()["pass_launches"]))
+        # two planes as well
+        psi = rng.standard_normal(eng.local_amps) + 1j * rng.standard_normal(eng.local_amps)
+        eng.set_state(psi)
+        eng.resolve_planes(*eng.plane_flags())
+        eng.step(0.5, 1)
+        results[-1] += (eng.get_state(),)
+        eng.close()
+    (a_state, a_sums, a_launches, a_c), (b_state, b_sums, b_launches, b_c) = results
+    assert a_launches == b_launches > 0
+    assert np.array_equal(a_state, b_state) and np.array_equal(a_sums, b_sums) and np.array_equal(a_c, b_c)
+    assert np.isfinite(a_state).all() and np.abs(a_state).max() > 0
