@@ -15,7 +15,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path() -> str:
-    return os.path.join(_PKG, "libqca_b200.so")
+    # QCA_B200_LIBRARY: another build of the SAME library (A/B timing of kernel variants, scratch/variants/); never a fallback
+    return os.environ.get("QCA_B200_LIBRARY") or os.path.join(_PKG, "libqca_b200.so")
 
 
 class QcaError(RuntimeError):

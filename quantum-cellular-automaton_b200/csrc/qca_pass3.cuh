@@ -168,6 +168,15 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
     };
     ract[0] = row_lookup(0);
     fetch_remote(0, ract[0], rp[0]);
+    // (sigma^- - sigma^+) sign of the flip of thread bit b as seen by this thread; only the flipped bits cost registers
+#ifdef QCA_V3_P0_SIGN_TABLE
+    constexpr bool SIGN_TABLE = true;
+#else
+    constexpr bool SIGN_TABLE = !FLIP_LOW;
+#endif
+    double sgn[kThrBits3];
+#pragma unroll
+    for (int b = 0; b < kThrBits3; ++b) sgn[b] = ((tid >> b) & 1u) ? -1.0 : 1.0;
 
 #pragma unroll
     for (int e = 0; e < kRows; ++e) {
@@ -177,19 +186,30 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
         }
         const unsigned row_act = ract[e & 1];
         const unsigned la0 = thr_act0 | row_act, la1 = thr_act1 | row_act;
-        double acc0 = 0.0, acc1 = 0.0;
+        // Later passes (SIGN_TABLE): written the way nvcc turns into ONE DFMA/DADD + two FSELs per amplitude and flip,
+        // with the predicates of a row moved into predicate registers wholesale (R2P).  Applying the thread's sign by
+        // XOR on the loaded pair instead (saves the +-1.0 table) makes nvcc wrap every partner LDS in a divergent
+        // branch: 6.8 instructions per amplitude and flip, 1736 instead of 1296 per thread and tile.  Pass 0 flips all
+        // nine thread bits; there the 18 registers of the table do not fit and the XOR form stays.
+        // Two accumulator pairs (partner threads / partner rows) halve the FP64 dependency chain.
+        double acc0 = 0.0, acc1 = 0.0, accr0 = 0.0, accr1 = 0.0;
         if (QLO == 0) {   // tile bit 0: the other half of the pair
-            if (la0 & 1u) acc0 += v[e].y;
-            if (la1 & 1u) acc1 -= v[e].x;
+            if (la0 & 1u) accr0 += v[e].y;
+            if (la1 & 1u) accr1 -= v[e].x;
         }
         // tile bits 1..9: partner thread, same row
 #pragma unroll
         for (int b = 0; b < kThrBits3; ++b) {
             if (b + 1 >= QLO) {
                 const double2 p = tile2[(e << kThrBits3) | (tid ^ (1u << b))];
-                const unsigned m = (tid << (31 - b)) & 0x80000000u;
-                if (la0 & (2u << b)) acc0 += sign_flip(p.x, m);
-                if (la1 & (2u << b)) acc1 += sign_flip(p.y, m);
+                if (SIGN_TABLE) {
+                    if (la0 & (2u << b)) acc0 = fma(p.x, sgn[b], acc0);
+                    if (la1 & (2u << b)) acc1 = fma(p.y, sgn[b], acc1);
+                } else {
+                    const unsigned m = (tid << (31 - b)) & 0x80000000u;
+                    if (la0 & (2u << b)) acc0 += sign_flip(p.x, m);
+                    if (la1 & (2u << b)) acc1 += sign_flip(p.y, m);
+                }
             }
         }
         // tile bits 10..13: partner row, same thread (registers)
@@ -198,14 +218,16 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
             if (kRowShift3 + k >= QLO) {
                 const double2 p = v[e ^ (1 << k)];
                 if ((e >> k) & 1) {
-                    if (la0 & (1u << (kRowShift3 + k))) acc0 -= p.x;
-                    if (la1 & (1u << (kRowShift3 + k))) acc1 -= p.y;
+                    if (la0 & (1u << (kRowShift3 + k))) accr0 -= p.x;
+                    if (la1 & (1u << (kRowShift3 + k))) accr1 -= p.y;
                 } else {
-                    if (la0 & (1u << (kRowShift3 + k))) acc0 += p.x;
-                    if (la1 & (1u << (kRowShift3 + k))) acc1 += p.y;
+                    if (la0 & (1u << (kRowShift3 + k))) accr0 += p.x;
+                    if (la1 & (1u << (kRowShift3 + k))) accr1 += p.y;
                 }
             }
         }
+        acc0 += accr0;
+        acc1 += accr1;
         // cluster bits: the pairs fetched one row ago
         if (CB) {
 #pragma unroll

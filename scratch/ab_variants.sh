@@ -1,0 +1,20 @@
+#!/bin/bash
+# A/B timing of library builds (scratch/variants/*.so) on ONE box: bench exact leg only, two rounds interleaved.
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_exact_gpu.py -m gpu -x -q 2>&1 | tail -3
+for round in 1 2; do
+for v in "$@"; do
+  QCA_B200_LIBRARY=$PWD/scratch/variants/libqca_$v.so timeout 200 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-matched --no-tdvp \
+      2> gpurun_out/ab_$v.err > gpurun_out/ab_${v}_$round.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/ab_${v}_$round.json"))
+    r = d["roofline"]
+    print("$v round $round: steps/s", round(d["value"], 4), "frac", round(r["frac"], 4), "ms by pass", [round(x, 3) for x in r["avg_launch_ms_by_pass"]],
+          "checksum", d["checksum"]["ok"], d["checksum"]["max_abs_diff_vs_committed"], "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+except Exception as e:
+    print("$v FAILED", e)
+PY
+done
+done

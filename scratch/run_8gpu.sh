@@ -1,12 +1,13 @@
 #!/bin/bash
-# One 8-GPU session: driver-independent parity log of the sharded path, then strong-scaling bench lines.
+# One 8-GPU session (charged 8x: keep it short): driver-independent parity log of the sharded path at 8 and 2
+# ranks, then strong-scaling bench lines with the persistent and the per-tile sharded kernels, N=33 on 8.
 mkdir -p gpurun_out
-python -m pytest tests/test_exact_multigpu.py -m gpu -q -rA 2>&1 | tail -25 > gpurun_out/r2_mgpu_pytest.log
+timeout 300 python -m pytest tests/test_exact_multigpu.py -m gpu -q -rA -k "8 or two_slot" 2>&1 | tail -25 > gpurun_out/r2_mgpu_pytest.log
 tail -8 gpurun_out/r2_mgpu_pytest.log
 run() {  # tag gpus extra-env...
   tag=$1; g=$2; shift 2
-  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 2961$g \
-      bench.py --gpus $g --steps ${STEPS:-4} --warmup 3 --no-e2e ${NCELLS:+--num-cells $NCELLS} 2> gpurun_out/r2_bench_${tag}.err | grep "^{" > gpurun_out/r2_bench_${tag}.json
+  env "$@" timeout ${TMO:-100} python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 2961$g \
+      bench.py --gpus $g --steps ${STEPS:-4} --warmup 3 --no-e2e --no-cpu-baseline --no-matched --no-tdvp ${NCELLS:+--num-cells $NCELLS} 2> gpurun_out/r2_bench_${tag}.err | grep "^{" > gpurun_out/r2_bench_${tag}.json
   python - <<PY
 import json
 try:
@@ -16,9 +17,13 @@ try:
           "nvlink GB/s", round(r["nvlink_read_gbs_per_gpu"], 1), "checksum ok", d["checksum"]["ok"], d["checksum"]["max_abs_diff_vs_committed"])
 except Exception as e:
     print("${tag} FAILED", e)
+    import subprocess
+    print(subprocess.run("grep -v 'OMP_NUM\|^\*\*\*' gpurun_out/r2_bench_${tag}.err | tail -6", shell=True, capture_output=True, text=True).stdout)
 PY
 }
 run 8gpu_persistent 8 QCA_X=1
 run 8gpu_per_tile 8 QCA_PERSISTENT_CTAS=0
+NCELLS=33 STEPS=2 TMO=150 run 8gpu_n33 8 QCA_X=1
+run 2gpu_persistent 2 QCA_X=1
+run 2gpu_per_tile 2 QCA_PERSISTENT_CTAS=0
 run 4gpu_persistent 4 QCA_X=1
-NCELLS=33 STEPS=2 run 8gpu_n33 8 QCA_X=1
