@@ -365,12 +365,18 @@ def b200_arm(args) -> None:
         rec = json.load(open(tpath)).get(f"N{args.num_cells}_g{world}")
         if rec and planes == rec.get("planes") and rec.get("passes_per_term", 3) == st["passes_per_apply"]:
             traffic = rec["dram_bytes_per_launch"]
+    # one GPU, >= 14 local qubits: 14-bit tiles, 512 threads, one CTA per SM (csrc/qca_pass3.cuh); sharded engines: 13-bit
+    # tiles with remote operand slots, persistent CTAs (csrc/qca_pass.cuh)
+    if world > 1:
+        kernel_name = "qca::pass_kernel_v2p / pass_kernel_v2" if st["local_bits"] >= 13 else "qca::pass_kernel_generic"
+    else:
+        kernel_name = "qca::pass_kernel_v3" if st["local_bits"] >= 14 else ("qca::pass_kernel_v2" if st["local_bits"] >= 13 else "qca::pass_kernel_generic")
     applies = max(pst["pass_launches"] // max(pst["passes_per_apply"], 1), 1)
     bytes_per_launch = pst["pass_bytes"] / max(pst["pass_launches"], 1)
     avg_ms = pst["profiled_pass_ms"] / max(pst["profiled_pass_launches"], 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": st.get("pass_kernel_name", "qca::pass_kernel_v2") + " (tile pass of the rule operator + fused Clenshaw update)",
+                "traffic": traffic, "kernel": kernel_name + " (tile pass of the rule operator + fused Clenshaw update)",
                 "avg_launch_ms_by_pass": [m / applies for m in pst["profiled_ms_by_pass"][:pst["passes_per_apply"]]],
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": pst["pass_launches"],
                 "peak_source": peak_src, "whole_step_gbs": whole_step_gbs, "per_gpu": True,
@@ -499,7 +505,9 @@ def e2e_leg(args, world, local_rank, make_engine, barrier, max_over_ranks) -> di
         host1.copy_(host0)
         e1 = make_engine(on_stream=s1.cuda_stream)
         e1.set_product_state(plist)
-        per_engine = (steps + 1) // 2
+        # the pipeline is timed over a longer batch than the sequential variant: its fill (first upload) and drain
+        # (last download) are part of the timed region and should not dominate it
+        per_engine = (max(1, args.e2e_steps) + 1) // 2
         run_sequential(e1, host1, 1)
         torch.cuda.synchronize()
         gate = th.Lock()

@@ -279,6 +279,17 @@ int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* wo
 int32_t qca_heff_expm(const qca_heff_t* h, const void* psi, void* out, int32_t krylov_dim, double t, double spectral_bound,
                       void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* Environment update of TDVP (algorithms/tdvp.py:329-347, `_update_left_environment` / `_update_right_environment`:
+ * three np.tensordot calls) on the same DMMA kernel:
+ *   out[r][m][s] = sum  Mx[(b,m),(a,w)] left[x][w][y] site[a][x][r] conj(site[b][y][s])
+ * h->left = the previous environment (dl, wl, dl), h->mix* = the ONE-site operator (g = 2), h->dr = the site
+ * tensor's other bond dimension; h->right is not read (pass h->left).  out: (dr, wr, dr).  A right
+ * environment is the same call on the mirrored tensors: site[a][u][l], W with its two bond indices swapped.
+ * Workspace: qca_env_grow_workspace_bytes(h).  Stream-ordered, no synchronisation. */
+int32_t qca_env_grow_workspace_bytes(const qca_heff_t* h, uint64_t* bytes);
+int32_t qca_env_grow(const qca_heff_t* h, const void* site, void* out, void* workspace, uint64_t workspace_bytes,
+                     void* stream);
+
 /* ------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The state is sharded over the top
  * log2(world_size) qubits; terms that flip a sharded qubit read the partner

@@ -118,6 +118,8 @@ SYMBOLS = {
     "qca_zgemm_profile": (C.c_int32, [C.c_int32, _dp, _dp, C.POINTER(C.c_uint64)]),
     "qca_heff_workspace_bytes": (C.c_int32, [C.POINTER(HeffStruct), C.c_int32, C.POINTER(C.c_uint64)]),
     "qca_heff_apply": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qca_env_grow_workspace_bytes": (C.c_int32, [C.POINTER(HeffStruct), C.POINTER(C.c_uint64)]),
+    "qca_env_grow": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "qca_heff_expm": (C.c_int32, [C.POINTER(HeffStruct), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                                   C.c_void_p, C.c_uint64, C.c_void_p]),
     "qca_exact_ipc_count": (C.c_int32, [C.c_void_p]),

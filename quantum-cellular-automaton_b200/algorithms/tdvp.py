@@ -38,7 +38,7 @@ import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
-from ..linalg import SiteOperator, gram_svd, heff_expm, householder_qr
+from ..linalg import SiteOperator, env_grow, gram_svd, heff_expm, householder_qr
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
@@ -120,7 +120,7 @@ class TDVP(Algorithm):
                 self._canonicalize(site - 1)
             # (2tdvp is gauge invariant: every tensor right of site 0 already is right-orthonormal,
             #  so the O(N^2) re-canonicalisations of the reference would only change gauge signs)
-            self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+            self._right[site] = self._grow_right(self._env_right(site + 1), site)
         self.heff_applications = 0
         self.heff_flops = 0.0      # real FP64 operations of the H_eff contractions (8 per complex MAC)
         self._gauge_dirty = False  # tensors and right environments are in the same gauge right now
@@ -186,7 +186,7 @@ class TDVP(Algorithm):
                 #  right environments match it: re-canonicalising would be a pure gauge change)
                 self._canonicalize(0)
                 for site in reversed(range(1, len(self._A))):
-                    self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+                    self._right[site] = self._grow_right(self._env_right(site + 1), site)
                 self._gauge_dirty = False
             self._sweep_right_two_site()
             self._sweep_left_two_site()
@@ -245,17 +245,13 @@ class TDVP(Algorithm):
     def _env_right(self, site):
         return self._one if site >= len(self._A) else self._right[site]
 
-    def _grow_left(self, prev, a, w):
-        torch = _torch()
-        t = torch.einsum("xwy,axr->awyr", prev, a)
-        t = torch.einsum("abwm,awyr->bmyr", w, t)
-        return torch.einsum("bmyr,bys->rms", t, a.conj())
+    def _grow_left(self, prev, site):
+        """Left environment including `site` (tdvp.py:329-337) on the DMMA kernel (csrc/qca_heff.cu, qca_env_grow)."""
+        return env_grow(prev, self._A[site], self._site_operator("one", site))
 
-    def _grow_right(self, prev, a, w):
-        torch = _torch()
-        t = torch.einsum("uwv,alu->awvl", prev, a)
-        t = torch.einsum("abmw,awvl->bmvl", w, t)
-        return torch.einsum("bmvl,bkv->lmk", t, a.conj())
+    def _grow_right(self, prev, site):
+        """Right environment including `site` (tdvp.py:339-347): the left update of the mirrored chain."""
+        return env_grow(prev, self._A[site].transpose(1, 2).contiguous(), self._site_operator("one_mirrored", site))
 
     # -- effective Hamiltonians, matrix-free ------------------------------------------------------------
     # (torch.einsum forms: only the dense route of tiny tensors uses them; everything else runs in
@@ -286,6 +282,8 @@ class TDVP(Algorithm):
         if op is None:
             if kind == "one":
                 op = SiteOperator(self._W_host[site], device=self.dev)
+            elif kind == "one_mirrored":   # bond indices swapped: right-environment updates
+                op = SiteOperator(np.ascontiguousarray(self._W_host[site].transpose(0, 1, 3, 2)), device=self.dev)
             elif kind == "two":
                 op = SiteOperator(self._W_host[site], self._W_host[site + 1], device=self.dev)
             else:
@@ -361,7 +359,7 @@ class TDVP(Algorithm):
             self._A[site] = ul.contiguous()
             self._A[site + 1] = (s[None, :, None] * vr).contiguous()
             if site < n - 2:
-                self._left[site] = self._grow_left(self._env_left(site - 1), self._A[site], self._W[site])
+                self._left[site] = self._grow_left(self._env_left(site - 1), site)
                 self._A[site + 1] = self._evolve_site(site + 1, -self.args.step_size / 2)
 
     def _sweep_left_two_site(self):
@@ -371,7 +369,7 @@ class TDVP(Algorithm):
             self._A[site] = vr.contiguous()
             self._A[site - 1] = (ul * s[None, None, :]).contiguous()
             if site > 1:
-                self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+                self._right[site] = self._grow_right(self._env_right(site + 1), site)
                 self._A[site - 1] = self._evolve_site(site - 1, -self.args.step_size / 2)
 
     # -- one-site TDVP (tdvp.py:65-105, 164-188) -----------------------------------------------------------
@@ -390,7 +388,7 @@ class TDVP(Algorithm):
                 continue
             q, c = self._left_qr(new, reduced=False)
             self._A[site] = self._fit(q, shape).contiguous()
-            self._left[site] = self._grow_left(self._env_left(site - 1), self._A[site], self._W[site])
+            self._left[site] = self._grow_left(self._env_left(site - 1), site)
             c = self._fit(c, (shape[2], c.shape[1]))
             c = self._evolve_bond(self._env_left(site), self._env_right(site + 1), c)
             self._A[site + 1] = torch.einsum("xl,plr->pxr", c, self._A[site + 1])
@@ -406,7 +404,7 @@ class TDVP(Algorithm):
                 continue
             q, c = self._right_qr(new, reduced=False)
             self._A[site] = self._fit(q, shape).contiguous()
-            self._right[site] = self._grow_right(self._env_right(site + 1), self._A[site], self._W[site])
+            self._right[site] = self._grow_right(self._env_right(site + 1), site)
             c = self._fit(c, (c.shape[0], shape[1]))
             c = self._evolve_bond(self._env_left(site - 1), self._env_right(site), c)
             self._A[site - 1] = torch.einsum("plr,rx->plx", self._A[site - 1], c)

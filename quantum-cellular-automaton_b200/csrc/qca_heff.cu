@@ -478,11 +478,10 @@ static int32_t he_plan(const qca_heff_t* h, int m, HeffPlan* p) {
     return QCA_OK;
 }
 
-// T1, T3 and the split-K partials of out = H_eff psi; the caller sums the ns2 partials at ws + off_p2
-static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* psi, double2* ws, cudaStream_t st) {
+// T1 = L . psi and T3 = (site operator) T1: the first two steps of H_eff psi (and of an environment update)
+static int32_t he_front(const qca_heff_t* h, const HeffPlan& p, const double2* psi, double2* ws, cudaStream_t st) {
     double2* t1 = ws + p.off_t1;
     double2* t3 = ws + p.off_t3;
-    double2* p2 = ws + p.off_p2;
     const int dl = h->dl, dr = h->dr, wl = h->wl, wr = h->wr, g = h->g;
     // structural zeros of the site operator(s): channels (g, w) of T1 nobody reads, channels (g', n) of T3
     // that are identically zero (two thirds of the work remain for the automaton's MPO)
@@ -504,6 +503,16 @@ static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* p
     he_mix_kernel<<<mix_blocks, HE_THREADS, 0, st>>>(t1, p.ns1, p.t1, t3, h->mix_rowptr, h->mix_col, (const double2*)h->mix_val,
                                                      g * wr, p.plane);
     QCA_CUDA(cudaGetLastError());
+    return QCA_OK;
+}
+
+// T1, T3 and the split-K partials of out = H_eff psi; the caller sums the ns2 partials at ws + off_p2
+static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* psi, double2* ws, cudaStream_t st) {
+    QCA_CHECK(he_front(h, p, psi, ws, st));
+    double2* t3 = ws + p.off_t3;
+    double2* p2 = ws + p.off_p2;
+    const int dl = h->dl, dr = h->dr, wl = h->wl, wr = h->wr, g = h->g;
+    const bool masks = h->use_masks && wl <= 32 && wr <= 32;
     // out[g][y][v] = sum_n sum_u T3[g][n][y][u] R[u][n][v]
     ZgemmArgs y{};
     y.a = t3; y.b = (const double2*)h->right; y.c = p2;
@@ -517,6 +526,34 @@ static int32_t he_apply(const qca_heff_t* h, const HeffPlan& p, const double2* p
         for (int i = 0; i < g; ++i) { y.chan_mask[i] = 1u; y.seg_mask[i] = h->row_mask[i]; }
     }
     QCA_CHECK(zgemm_launch(y, st));
+    return QCA_OK;
+}
+
+// ---- environment update (algorithms/tdvp.py:329-347) ----------------------------------------------------
+// E'[r][m][s] = sum_{b,y} T3[b][m][y][r] conj(A[b][y][s]),  T3 = (site operator)(E . A): the front of H_eff applied to
+// the site tensor A, then one more DMMA contraction with conj(A) instead of the other environment.
+__global__ void __launch_bounds__(HE_THREADS)
+he_conj_kernel(double2* __restrict__ dst, const double2* __restrict__ src, long long n) {
+    for (long long s = (long long)blockIdx.x * HE_THREADS + threadIdx.x; s < n; s += (long long)gridDim.x * HE_THREADS) {
+        const double2 v = src[s];
+        dst[s] = make_double2(v.x, -v.y);
+    }
+}
+
+struct GrowPlan {
+    HeffPlan hp;
+    int ns3;
+    long long out_elems, off_conj, off_p3, total;
+};
+
+static int32_t grow_plan(const qca_heff_t* h, GrowPlan* g) {
+    QCA_CHECK(he_plan(h, 0, &g->hp));
+    QCA_REQUIRE(h->g == 2, QCA_ERR_ARG, "environment updates take a one-site operator (g = 2)");
+    g->out_elems = (long long)h->dr * h->wr * h->dr;
+    g->ns3 = he_split(h->dr, h->dr, h->wr, 2ll * ((h->dl + 15) / 16), g->hp.sms);
+    g->off_conj = g->hp.total;
+    g->off_p3 = g->off_conj + g->hp.dim;
+    g->total = g->off_p3 + g->out_elems * g->ns3;
     return QCA_OK;
 }
 
@@ -543,6 +580,44 @@ int32_t qca_heff_apply(const qca_heff_t* h, const void* psi, void* out, void* wo
     QCA_CHECK(qca::he_apply(h, p, (const double2*)psi, ws, st));
     const int blocks = (int)std::max<long long>(1, std::min<long long>((p.dim + qca::HE_THREADS - 1) / qca::HE_THREADS, 8ll * p.sms));
     qca::he_sum_kernel<<<blocks, qca::HE_THREADS, 0, st>>>((double2*)out, ws + p.off_p2, p.ns2, p.dim, p.dim);
+    QCA_CUDA(cudaGetLastError());
+    return QCA_OK;
+}
+
+int32_t qca_env_grow_workspace_bytes(const qca_heff_t* h, uint64_t* bytes) {
+    QCA_REQUIRE(bytes, QCA_ERR_ARG, "NULL argument");
+    qca::GrowPlan g{};
+    QCA_CHECK(qca::grow_plan(h, &g));
+    *bytes = (uint64_t)g.total * sizeof(double2);
+    return QCA_OK;
+}
+
+int32_t qca_env_grow(const qca_heff_t* h, const void* site, void* out, void* workspace, uint64_t workspace_bytes,
+                     void* stream) {
+    using namespace qca;
+    QCA_REQUIRE(site && out && workspace, QCA_ERR_ARG, "NULL argument");
+    GrowPlan g{};
+    QCA_CHECK(grow_plan(h, &g));
+    QCA_REQUIRE(workspace_bytes >= (uint64_t)g.total * sizeof(double2), QCA_ERR_ARG, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* ws = (double2*)workspace;
+    const HeffPlan& p = g.hp;
+    const int dl = h->dl, dr = h->dr, wr = h->wr;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((p.dim + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
+    he_conj_kernel<<<blocks, HE_THREADS, 0, st>>>(ws + g.off_conj, (const double2*)site, p.dim);
+    QCA_CUDA(cudaGetLastError());
+    QCA_CHECK(he_front(h, p, (const double2*)site, ws, st));
+    // C_m[r][s] = sum_b sum_y T3[b][m][y][r] conj(A)[b][y][s]   (batch m, segments b; A operand with r contiguous)
+    ZgemmArgs z{};
+    z.a = ws + p.off_t3; z.b = ws + g.off_conj; z.c = ws + g.off_p3;
+    z.M = dr; z.N = dr; z.K = dl; z.S = 2; z.G = wr;
+    z.a_sg = (long long)dl * dr; z.a_ss = (long long)wr * dl * dr; z.a_sm = 1; z.a_sk = dr;
+    z.b_sg = 0; z.b_ss = (long long)dl * dr; z.b_sk = dr;
+    z.c_sg = dr; z.c_sm = (long long)wr * dr;
+    z.nsplit = g.ns3; z.c_ssplit = g.out_elems;
+    QCA_CHECK(zgemm_launch(z, st));
+    const int ob = (int)std::max<long long>(1, std::min<long long>((g.out_elems + HE_THREADS - 1) / HE_THREADS, 8ll * p.sms));
+    he_sum_kernel<<<ob, HE_THREADS, 0, st>>>((double2*)out, ws + g.off_p3, g.ns3, g.out_elems, g.out_elems);
     QCA_CUDA(cudaGetLastError());
     return QCA_OK;
 }

@@ -266,6 +266,29 @@ def heff_apply(left, right, op: SiteOperator, psi):
     return out
 
 
+def env_grow(prev, site, op: SiteOperator):
+    """Environment update (tdvp.py:329-347) on the DMMA kernel:
+    out[r, m, s] = sum  W[a, b, w, m] prev[x, w, y] site[a, x, r] conj(site[b, y, s])
+    with `op` the one-site operator of W.  A right environment is the same call on the mirrored tensors
+    (site[a, u, l], W with its bond indices swapped)."""
+    import torch
+    assert prev.is_cuda and prev.dtype == torch.complex128 and site.dtype == torch.complex128
+    dl, wl, dl2 = prev.shape
+    g, dx, dr = site.shape
+    assert g == 2 and op.g == 2 and dx == dl == dl2 and wl == op.wl, (prev.shape, site.shape, op.g, op.wl)
+    prev, site = prev.contiguous(), site.contiguous()
+    h = _lib.HeffStruct(prev.data_ptr(), prev.data_ptr(), op.rowptr.data_ptr(), op.col.data_ptr(), op.val.data_ptr(),
+                        dl, dr, wl, op.wr, 2, int(op.use_masks), (C.c_uint32 * 4)(*op.col_mask), (C.c_uint32 * 4)(*op.row_mask))
+    nbytes = C.c_uint64()
+    _lib.check(_lib.lib.qca_env_grow_workspace_bytes(C.byref(h), C.byref(nbytes)))
+    ws = _Workspace.get(nbytes.value, site.device)
+    out = torch.empty((dr, op.wr, dr), dtype=site.dtype, device=site.device)
+    stream = torch.cuda.current_stream(site.device).cuda_stream
+    _lib.check(_lib.lib.qca_env_grow(C.byref(h), C.c_void_p(site.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream)))
+    return out
+
+
 def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float, spectral_bound: float = 0.0):
     """exp(-i t H_eff) psi by `krylov_dim` Lanczos steps, all on the device, no host synchronisation.
     spectral_bound: a bound of ||H_eff|| if known (the small exponential then is a Chebyshev series)."""

@@ -18,3 +18,6 @@ except Exception as e:
 PY
 done
 done
+# TDVP: parity tests and the chi = 256 step breakdown with the in-tree build
+timeout 600 python -m pytest tests/test_tdvp_gpu.py -m gpu -x -q 2>&1 | tail -4
+timeout 200 python scratch/tdvp_prof2.py > gpurun_out/r2c_tdvp_prof.txt 2>&1; head -12 gpurun_out/r2c_tdvp_prof.txt; tail -1 gpurun_out/r2c_tdvp_prof.txt

@@ -53,6 +53,13 @@ TDVP_CASES = [
     ("tdvp1_eqsup7", "1tdvp", 7, 1, 1, 2, "equal_superposition", 40, 0.005, 8, 5e-5, 10.0),
     ("tdvp2_eqsup8_d2", "2tdvp", 8, 2, 2, 4, "equal_superposition", 30, 0.005, 6, 1e-6, 10.0),
     ("tdvp2_gradient9_chi4", "2tdvp", 9, 1, 1, 3, "gradient", 40, 0.01, 4, 1e-4, 5.0),
+    # round 2: 12 measured rows each (plotting frequency 50 -> every 4th step); BASELINE configs[2]'s shape
+    # (2tdvp, single, 15 cells) at a bond cap and step count the reference's dense H_eff finishes in seconds
+    ("tdvp2_single15_chi8", "2tdvp", 15, 1, 1, 2, "single", 48, 0.005, 8, 5e-5, 50.0),
+    ("tdvp2_gradient12_rows12", "2tdvp", 12, 1, 1, 2, "gradient", 48, 0.005, 8, 5e-5, 50.0),
+    # (1tdvp pads every bond of this product state to the cap with Householder completions of zero columns: the
+    #  reference's own numbers are reproducible to ~1e-7 only -- "padded" fixtures are compared at 1e-6)
+    ("tdvp1_padded_gradient10_rows12", "1tdvp", 10, 1, 1, 2, "gradient", 48, 0.005, 8, 5e-5, 50.0),
 ]
 
 HPSI_CASES = [

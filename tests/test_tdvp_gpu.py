@@ -15,6 +15,11 @@ from conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 WELL_CONDITIONED = ("eqsup", "gradient")
+PADDED = ("padded",)   # 1tdvp from a product state far below the bond cap: reproducible to ~1e-7 only (Householder completions of zero columns)
+
+
+def well(name):
+    return any(k in name for k in WELL_CONDITIONED) and not any(k in name for k in PADDED)
 
 
 def replay(spec, g, algorithm_cls=None):
@@ -41,7 +46,7 @@ def oracle_run(spec, g, **kw):
                                 int(g["plot_step_interval"]), spec["chi"], spec["eps"], **kw)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if n.startswith("tdvp1") and any(k in n for k in WELL_CONDITIONED)])
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if n.startswith("tdvp1") and well(n)])
 def test_1tdvp_matches_reference_run(name):
     """1tdvp has no SVD: with LAPACK-convention QR the reference's numbers are reproduced."""
     spec, g = load_golden(name)
@@ -61,13 +66,13 @@ def test_2tdvp_matches_gauge_consistent_oracle_and_reference_within_its_spread(n
     spec, g = load_golden(name)
     pop, sse, bond, algo = replay(spec, g)
     pop_o, ent_o, bond_o, psi_o = oracle_run(spec, g, consistent=True)
-    well = any(k in name for k in WELL_CONDITIONED)
-    tol = 1e-8 if well else 2e-5   # 0/1 product states: zero Schmidt values, see test_tdvp_oracle.py
-    if well:
+    well_c = well(name)
+    tol = 1e-8 if well_c else 2e-5   # 0/1 product states: zero Schmidt values, see test_tdvp_oracle.py
+    if well_c:
         assert np.array_equal(bond, bond_o)
     assert np.abs(pop - pop_o).max() < tol
-    assert np.abs(sse - ent_o).max() < (tol if well else 2e-4)
-    if well:
+    assert np.abs(sse - ent_o).max() < (tol if well_c else 2e-4)
+    if well_c:
         assert abs(abs(np.vdot(algo.psi.as_vector(), psi_o)) - 1.0) < 1e-8
     spread_p, spread_e = float(g["gauge_spread_population"]), float(g["gauge_spread_entropy"])
     assert np.abs(pop - g["population"]).max() < max(3 * spread_p, 2e-5)
@@ -75,12 +80,13 @@ def test_2tdvp_matches_gauge_consistent_oracle_and_reference_within_its_spread(n
     assert np.abs(bond - g["bond_dims"]).max() <= 1
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if n.startswith("tdvp1") and not any(k in n for k in WELL_CONDITIONED)])
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if n.startswith("tdvp1") and not well(n)])
 def test_1tdvp_basis_states_within_reference_reproducibility(name):
     spec, g = load_golden(name)
     pop, sse, bond, algo = replay(spec, g)
-    assert np.abs(pop - g["population"]).max() < 2e-5
-    assert np.abs(sse - g["single_site_entropy"]).max() < 2e-4
+    tol = 1e-6 if any(k in name for k in PADDED) else 2e-5
+    assert np.abs(pop - g["population"]).max() < tol
+    assert np.abs(sse - g["single_site_entropy"]).max() < 10 * tol
     assert np.abs(bond - g["bond_dims"]).max() <= 1
 
 
@@ -230,6 +236,36 @@ def test_native_heff_apply_matches_einsum(dl, dr, distance):
     assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("dl,dr,distance", [(1, 2, 1), (3, 5, 1), (16, 16, 1), (40, 24, 2), (64, 64, 1), (130, 96, 1)])
+def test_native_environment_update_matches_einsum(dl, dr, distance):
+    """qca_env_grow (front of H_eff + one DMMA contraction with conj(A)) against the reference's three
+    tensordots (tdvp.py:329-347), for a left environment and -- through the mirrored tensors -- a right one."""
+    import torch
+    from qca_b200.linalg import SiteOperator, env_grow
+    w1, _ = _mpo_pair(distance=distance, lo=distance, hi=2 * distance)
+    wl, wr = w1.shape[2], w1.shape[3]
+    gen = torch.Generator(device="cuda").manual_seed(dl * 77 + dr)
+    def rnd(*shape):
+        return torch.randn(*shape, dtype=torch.complex128, device="cuda", generator=gen)
+    w = torch.as_tensor(w1, device="cuda")
+    # left: prev[x,w,y], a[a,x,r]
+    prev, a = rnd(dl, wl, dl), rnd(2, dl, dr)
+    t = torch.einsum("xwy,axr->awyr", prev, a)
+    t = torch.einsum("abwm,awyr->bmyr", w, t)
+    want = torch.einsum("bmyr,bys->rms", t, a.conj())
+    got = env_grow(prev, a, SiteOperator(w1, device="cuda"))
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+    # right: prev[u,w,v] with w the RIGHT bond of W, a[a,l,u]
+    prev, a = rnd(dl, wr, dl), rnd(2, dr, dl)
+    t = torch.einsum("uwv,alu->awvl", prev, a)
+    t = torch.einsum("abmw,awvl->bmvl", w, t)
+    want = torch.einsum("bmvl,bkv->lmk", t, a.conj())
+    got = env_grow(prev, a.transpose(1, 2).contiguous(), SiteOperator(np.ascontiguousarray(w1.transpose(0, 1, 3, 2)), device="cuda"))
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+
+
 @pytest.mark.parametrize("chi,m,t", [(4, 24, 0.3), (8, 40, 1.1), (12, 12, 0.02), (8, 64, 2.0)])
 def test_native_krylov_exponential_matches_dense(chi, m, t):
     """qca_heff_expm (Lanczos + Jacobi on the device) against exp(-i t H_eff) psi with H_eff assembled
@@ -247,7 +283,7 @@ def test_native_krylov_exponential_matches_dense(chi, m, t):
     # left environments up to the middle of the chain
     for site in range(n // 2 - 1):
         algo._shift_right(site)
-        algo._left[site] = algo._grow_left(algo._env_left(site - 1), algo._A[site], algo._W[site])
+        algo._left[site] = algo._grow_left(algo._env_left(site - 1), site)
     i = n // 2 - 1
     left, right = algo._env_left(i - 1), algo._env_right(i + 2)
     theta = torch.einsum("alm,bmr->ablr", algo._A[i], algo._A[i + 1])

