@@ -638,6 +638,9 @@ def tdvp_leg(args, device: int) -> dict:
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     flops, napply = algo.heff_flops, algo.heff_applications
+    spec_stats = {"speculative_splits": int(algo.speculative_splits), "repeated_steps": int(algo.repeated_steps),
+                  "note": "splits at the bond cap run without a host read (cuSOLVER zheevd called directly, flags checked once per "
+                          "step); counted over warm-up + timed steps"}
     # the contraction kernel itself, in situ: one more time step with an event pair around every
     # launch of the DMMA kernel (all bond sizes of the chain, L2 state as in the real sweep)
     _lib.zgemm_profile(True)
@@ -698,6 +701,7 @@ def tdvp_leg(args, device: int) -> dict:
             "config": {"workload": f"2tdvp, --num-cells {n}, --max-bond-dim {chi}, distance 1, interval [1,2), step 0.005, "
                                    "seeded random MPS at the bond cap, svd_epsilon 1e-14", "max_bond": int(max(dims))},
             "heff_applications_per_step": napply / args.tdvp_steps, "centre_norm_error": norm_err,
+            "split": spec_stats,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": dgemm_tflops, "unit": "TFLOP/s",
                          "frac": achieved / dgemm_tflops, "traffic": None,
                          "kernel": "qca::zgemm_dmma_kernel (L.psi and T.R contractions of H_eff, FP64 tensor cores)",

@@ -33,12 +33,13 @@ Index conventions are the reference's: ``A[p,l,r]``, ``W[a,b,wl,wr]``, environme
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
 from .algorithm import Algorithm
 from .. import _lib
-from ..linalg import SiteOperator, env_grow, gram_svd, heff_expm, householder_qr
+from ..linalg import SiteOperator, env_grow, gram_svd, gram_svd_at_cap, heff_expm, householder_qr
 from ..tensor_networks import MPS, MPO
 
 DENSE_LIMIT = 64          # effective dimension up to which H_eff is exponentiated densely
@@ -124,6 +125,15 @@ class TDVP(Algorithm):
         self.heff_applications = 0
         self.heff_flops = 0.0      # real FP64 operations of the H_eff contractions (8 per complex MAC)
         self._gauge_dirty = False  # tensors and right environments are in the same gauge right now
+        # 2tdvp at the bond cap: a split whose truncation was decided by the cap in the previous time step is computed
+        # speculatively (no host read); the step's flags are read once at its end and the step is repeated with the
+        # synchronising split if any of them is false
+        self._speculate = os.environ.get("QCA_TDVP_SYNC_SPLIT") is None
+        self._decided: dict = {}   # (left site, sweep direction) -> the last split there kept exactly the cap
+        self._spec_flags: list = []
+        self._speculating = False
+        self.speculative_splits = 0
+        self.repeated_steps = 0
 
     # -- Algorithm interface ----------------------------------------------------------------
     @property
@@ -188,8 +198,20 @@ class TDVP(Algorithm):
                 for site in reversed(range(1, len(self._A))):
                     self._right[site] = self._grow_right(self._env_right(site + 1), site)
                 self._gauge_dirty = False
+            snapshot = (list(self._A), list(self._left), list(self._right))   # tensors are replaced, never written in place
+            self._spec_flags = []
+            self._speculating = self._speculate
             self._sweep_right_two_site()
             self._sweep_left_two_site()
+            if self._spec_flags:
+                torch = _torch()
+                if not bool(torch.stack(self._spec_flags).all().item()):   # the one host read of a step at the cap
+                    self._A, self._left, self._right = (list(x) for x in snapshot)
+                    self._decided.clear()
+                    self._speculating = False
+                    self.repeated_steps += 1
+                    self._sweep_right_two_site()
+                    self._sweep_left_two_site()
         else:
             self._canonicalize(0)
             self._sweep_right_one_site()
@@ -338,14 +360,22 @@ class TDVP(Algorithm):
         # tail norm is under eps (tdvp.py:290-292) always lies inside the resolved part
         eps = self.args.svd_epsilon
         cap = min(self.args.max_bond_dim, 2 * min(dl, dr))
-        info = {}
-        u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))), need=cap, tail_floor=eps, info=info)
-        if info.get("decided"):
-            keep = cap       # everything beyond the cap still weighs >= eps: no need to look at the tail (no host sync)
+        key = (i, self._sweep_dir)
+        if self._speculating and self._decided.get(key) and cap <= min(mat.shape):
+            u, s, vh, ok = gram_svd_at_cap(mat, cap, eps)
+            self._spec_flags.append(ok)
+            self.speculative_splits += 1
+            keep = cap
         else:
-            tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
-            below = (tail < eps).nonzero()
-            keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
+            info = {}
+            u, s, vh, rest = gram_svd(mat, stop_below=eps / (4.0 * math.sqrt(min(mat.shape))), need=cap, tail_floor=eps, info=info)
+            if info.get("decided"):
+                keep = cap       # everything beyond the cap still weighs >= eps: no need to look at the tail (no host sync)
+            else:
+                tail = torch.sqrt(torch.flip(torch.cumsum(torch.flip(s * s, [0]), 0), [0]) + rest * rest)
+                below = (tail < eps).nonzero()
+                keep = min(int(below[0, 0]) if below.numel() else cap, cap, s.shape[0])
+            self._decided[key] = bool(info.get("decided_level0")) and keep == cap
         ul = u.reshape(2, dl, -1)[:, :, :keep]
         vr = vh.reshape(-1, 2, dr).permute(1, 0, 2)[:, :keep, :]
         sk = s[:keep] / torch.linalg.vector_norm(s[:keep])
@@ -354,19 +384,21 @@ class TDVP(Algorithm):
     def _sweep_right_two_site(self):
         torch = _torch()
         n = len(self._A)
+        self._sweep_dir = 0
         for site in range(n - 1):
             ul, s, vr = self._two_site(site, site + 1)
             self._A[site] = ul.contiguous()
-            self._A[site + 1] = (s[None, :, None] * vr).contiguous()
+            self._A[site + 1] = (s[None, :, None] * vr).resolve_conj().contiguous()
             if site < n - 2:
                 self._left[site] = self._grow_left(self._env_left(site - 1), site)
                 self._A[site + 1] = self._evolve_site(site + 1, -self.args.step_size / 2)
 
     def _sweep_left_two_site(self):
         n = len(self._A)
+        self._sweep_dir = 1
         for site in reversed(range(1, n)):
             ul, s, vr = self._two_site(site - 1, site)
-            self._A[site] = vr.contiguous()
+            self._A[site] = vr.resolve_conj().contiguous()   # (vh comes as a lazily conjugated view)
             self._A[site - 1] = (ul * s[None, None, :]).contiguous()
             if site > 1:
                 self._right[site] = self._grow_right(self._env_right(site + 1), site)

@@ -196,6 +196,27 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Stage a tile global -> shared with bulk copies (TMA engine): one per contiguous piece of 2^L doubles (at most 8 KiB),
+// all completing on one mbarrier, which every thread then waits for.  Replaces one LDG.128 per thread and register
+// row: on one GPU this took the 14-bit kernel from 0.79 to 0.86 of the measured HBM peak (ncu had shown the LSU's
+// instruction queue -- lg_throttle -- pacing the staging, not DRAM; profiles/r02_ab_v3_*.json).
+// `bar` must have been initialised with count 1; `parity` is the phase this use completes (0, 1, 0, ... per use).
+template <typename I, int L, int TILE_BITS, int THREADS>
+__device__ __forceinline__ void stage_tile_bulk(double* tile, const double* in, I base, int H0, unsigned tid, unsigned bar,
+                                                unsigned parity) {
+    constexpr int PIECE_BITS = L < 10 ? L : 10;
+    constexpr int NPIECES = 1 << (TILE_BITS - PIECE_BITS);
+    constexpr unsigned low_mask = (1u << L) - 1u;
+    if (tid == 0) mbar_arrive_expect_tx(bar, 8u << TILE_BITS);
+#pragma unroll 1
+    for (int r = (int)tid; r < NPIECES; r += THREADS) {
+        const unsigned y = (unsigned)r << PIECE_BITS;   // tile-local index of the first amplitude of the piece
+        const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+        bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, bar);
+    }
+    mbar_wait(bar, parity);
+}
+
 // Epilogue operands are streamed through rings of shared memory, kRingRowsTotal rows of 4 KiB
 // (256 threads x 16 B), filled from kernel entry on: deep memory-level parallelism at no register cost.
 //   * local operands (HBM, ~1 us): per-thread cp.async, one commit group per row;
@@ -344,10 +365,23 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2(const PassArgs
     }
     // ---- stage the tile: 16 rows x one 16-byte pair per thread -------------------------------
     double2 v[kRows];
+    if (NREM) {   // sharded launches: bulk copies (the mbarrier sits in the unused upper half of the mbarrier row)
+        const unsigned tile_bar = smem_u32(ring + (kRingRowsTotal - 1) * kPassThreads) + 2048u;
+        if (tid == 0) {
+            mbar_init(tile_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        stage_tile_bulk<I, L, kTile, kPassThreads>(tile, in, base, H0, tid, tile_bar, 0u);
 #pragma unroll
-    for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + row_x(e));
+        for (int e = 0; e < kRows; ++e) v[e] = tile2[(e << (kRowShift - 1)) | tid];
+    } else {
 #pragma unroll
-    for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
+        for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + row_x(e));
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
+    }
 
     // ---- rule predicate words ------------------------------------------------------------------
     // la[j] bit q: local bit q of element (e, j) is flipped by an active term
@@ -497,11 +531,12 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2p(const PassArg
     const unsigned piece = lane / CHUNK_LANES;
 
     // everything that depends on the tile
-    struct TileCtx { I x_thr; unsigned act[NREM]; unsigned rot0, rot1; };
+    struct TileCtx { I base, x_thr; unsigned act[NREM]; unsigned rot0, rot1; };
     auto setup = [&](unsigned long long t, TileCtx& c) {
         const I t_lo = (I)(t & ((1ull << gap) - 1ull));
         const I t_hi = (I)(t >> gap);
         const I base = (t_lo << L) | (t_hi << (H0 + M));
+        c.base = base;
         c.x_thr = base | (I)(y_thr & low_mask) | ((I)(y_thr >> L) << H0);
         c.rot0 = c.rot1 = 0;
 #pragma unroll
@@ -568,10 +603,13 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2p(const PassArg
 #pragma unroll
     for (int k = 0; k < NREM; ++k) carry[k] = 0;
     // ---- prologue: barriers, first rows of the first tile ----------------------------------------------
+    const unsigned tile_bar = smem_u32(ring + (kRingRowsTotal - 1) * kPassThreads) + 2048u;   // upper half of the mbarrier row
     if (lane < ISSUERS * NBAR) mbar_init(mbar0 + lane * 8u, 1);
+    if (tid == 0) mbar_init(tile_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
+    __syncthreads();
+    unsigned tile_phase = 0;
 #pragma unroll
     for (int e = 0; e < DC; ++e) remote_issue(cur, e);
     if (NUNC) {
@@ -589,12 +627,12 @@ __global__ void __launch_bounds__(kPassThreads, 2) pass_kernel_v2p(const PassArg
         const unsigned long long t_next = t + gridDim.x;
         const bool has_next = t_next < a.ntiles;   // uniform over the CTA
         if (has_next) setup(t_next, nxt);
-        // ---- stage the tile ------------------------------------------------------------------------
+        // ---- stage the tile: bulk copies onto one mbarrier (stage_tile_bulk), then the thread's 16 pairs ------------
         double2 v[kRows];
+        stage_tile_bulk<I, L, kTile, kPassThreads>(tile, in, cur.base, H0, tid, tile_bar, tile_phase);
+        tile_phase ^= 1u;
 #pragma unroll
-        for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + (cur.x_thr | row_off(e)));
-#pragma unroll
-        for (int e = 0; e < kRows; ++e) tile2[(e << (kRowShift - 1)) | tid] = v[e];
+        for (int e = 0; e < kRows; ++e) v[e] = tile2[(e << (kRowShift - 1)) | tid];
         unsigned lo_act0 = 0, lo_act1 = 0;
         if (FLIP_LOW) {
             const unsigned w = ((unsigned)cur.x_thr & 0x1ffu) << d;

@@ -31,7 +31,8 @@ constexpr int kRowShift3 = kTile3 - kRegHigh;    // 10: tile bits 10..13 are reg
 constexpr int kThrBits3 = kRowShift3 - 1;        // 9 thread bits (tile bits 1..9)
 constexpr int kMaxClusterBits = 3;               // portable cluster size 8
 constexpr int kRing3Rows = 12;                   // 8 KiB each
-constexpr int kPass3SmemBytes = (8 << kTile3) + kRing3Rows * kPass3Threads * 16;   // 224 KiB
+constexpr int kPass3TileRingBytes = (8 << kTile3) + kRing3Rows * kPass3Threads * 16;   // 224 KiB
+constexpr int kPass3SmemBytes = kPass3TileRingBytes + 16;   // + the mbarrier of the bulk-copied tile
 
 struct Pass3Args {
     const double* in[2];
@@ -127,10 +128,40 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
     }
     // ---- stage the tile --------------------------------------------------------------------------------
     double2 v[kRows];
+#ifndef QCA_V3_LDG_TILE
+    // The tile goes global -> shared by bulk copies (TMA engine), one per contiguous piece (2^L doubles, at most 8 KiB),
+    // all completing on one mbarrier; the threads then read their 16 pairs from shared memory.  Instead of 16 LDG.128
+    // per thread (ncu, round 2: lg_throttle 3.1-3.4 stalled warps per issue next to long_scoreboard 4.4 -- the
+    // load/store unit's instruction queue, not DRAM, paced the staging) the LSU sees no global load for the tile at all.
+    // Measured at N = 30 on one B200, same box, interleaved runs (profiles/r02_ab_v3_*.json): pass 0 6.59 -> 5.49 ms
+    // (6.26 TB/s, 0.96 of the measured copy peak), later passes 5.03 -> 4.79 and 5.08 -> 4.94 ms, 0.831 -> 0.911 steps/s.
+    {
+        const unsigned tile_bar = smem_u32(tile) + (unsigned)kPass3TileRingBytes;
+        if (tid == 0) {
+            mbar_init(tile_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(tile_bar, 8u << kTile3);
+        constexpr int PIECE_BITS = L < 10 ? L : 10;
+        constexpr int NPIECES = 1 << (kTile3 - PIECE_BITS);
+#pragma unroll 1
+        for (int r = (int)tid; r < NPIECES; r += kPass3Threads) {
+            const unsigned y = (unsigned)r << PIECE_BITS;   // tile-local index of the first amplitude of the piece
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, tile_bar);
+        }
+        mbar_wait(tile_bar, 0);
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) v[e] = tile2[(e << kThrBits3) | tid];
+    }
+#else
 #pragma unroll
     for (int e = 0; e < kRows; ++e) v[e] = ldg_stream(in + row_x(e));
 #pragma unroll
     for (int e = 0; e < kRows; ++e) tile2[(e << kThrBits3) | tid] = v[e];
+#endif
 
     // ---- thread-constant predicate words ---------------------------------------------------------------
     unsigned thr_act0 = 0, thr_act1 = 0;
@@ -151,7 +182,9 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
         cluster_arrive();   // my tile is staged ...
         cluster_wait();     // ... and so is everybody else's (also orders this CTA's own stores: no __syncthreads needed)
     } else {
-        __syncthreads();
+#ifdef QCA_V3_LDG_TILE
+        __syncthreads();    // (bulk-copied tile: every thread has waited for the tile's mbarrier itself)
+#endif
     }
     // Row predicates and the partner CTAs' pairs are fetched ONE ROW AHEAD: a distributed-shared-memory load takes
     // ~200+ cycles, and issued where it is consumed it was 45 % of the row time (ncu source page, round 2).
@@ -201,7 +234,10 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
 #pragma unroll
         for (int b = 0; b < kThrBits3; ++b) {
             if (b + 1 >= QLO) {
-                const double2 p = tile2[(e << kThrBits3) | (tid ^ (1u << b))];
+                double2 p = tile2[(e << kThrBits3) | (tid ^ (1u << b))];
+#ifndef QCA_V3_LDG_TILE
+                asm volatile("" : "+d"(p.x), "+d"(p.y));   // pins the LDS here: never sunk into a (divergent) branch
+#endif
                 if (SIGN_TABLE) {
                     if (la0 & (2u << b)) acc0 = fma(p.x, sgn[b], acc0);
                     if (la1 & (2u << b)) acc1 = fma(p.y, sgn[b], acc1);

@@ -7,6 +7,12 @@ import math
 from . import _lib
 
 
+def _plain(t):
+    """Contiguous tensor whose MEMORY holds its values: torch's lazy conjugation (`x.conj()` only sets a flag, and
+    `.contiguous()` keeps it) must be materialised before a raw pointer goes to the C library."""
+    return t.resolve_conj().resolve_neg().contiguous()
+
+
 def householder_qr(mat, complete: bool = False):
     """QR of a complex128 CUDA matrix with LAPACK's Householder sign convention -- the factors
     numpy.linalg.qr(mat, mode='reduced' | 'complete') returns (csrc/qca_linalg.cu).  Returns (q, r)
@@ -15,7 +21,7 @@ def householder_qr(mat, complete: bool = False):
     assert mat.is_cuda and mat.dtype == torch.complex128 and mat.dim() == 2
     m, n = mat.shape
     kq = m if complete else min(m, n)
-    a = mat.T.clone(memory_format=torch.contiguous_format)     # row-major (n, m) == column-major (m, n)
+    a = mat.resolve_conj().T.clone(memory_format=torch.contiguous_format)     # row-major (n, m) == column-major (m, n)
     tau = torch.empty(min(m, n), dtype=mat.dtype, device=mat.device)
     q = torch.empty((kq, m), dtype=mat.dtype, device=mat.device)   # column-major m x kq
     r = torch.empty((n, kq), dtype=mat.dtype, device=mat.device)   # column-major kq x n
@@ -98,6 +104,7 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
                 rest_norm = torch.sqrt((lam[keep:]).sum())
                 if info is not None:
                     info["decided"] = True
+                    info["decided_level0"] = level == 0   # what gram_svd_at_cap reproduces without a host read
                 break
             rest = torch.linalg.vector_norm(mat @ basis)      # accurate route (one more host sync)
             beyond = torch.cat(ss)[need:]
@@ -109,6 +116,95 @@ def gram_svd(mat, stop_below: float = 0.0, level_ratio: float = 1e-3, max_levels
     u, s, v = torch.cat(us, dim=1), torch.cat(ss), torch.cat(vs, dim=1)
     order = torch.argsort(s, descending=True, stable=True)    # levels are ordered; ties inside noise only
     return u[:, order], s[order], v[:, order].conj().T, rest_norm
+
+
+class _CusolverEigh:
+    """Hermitian eigendecomposition WITHOUT a host synchronisation: cuSOLVER's ``zheevd`` called directly (ctypes, the
+    library torch has already loaded) on the caller's stream, `devInfo` left on the device.  ``torch.linalg.eigh`` runs
+    the same routine but reads `info` back after every call, which drains the stream twice per 2TDVP split (that and
+    the truncation decision: 15 % of a chi = 256 time step was idle GPU).  Library code, like torch.linalg.eigh: the
+    eigensolver is the one step of the 2TDVP split that is not native ("the split")."""
+    _solver = None
+    _handles = {}
+    _work = {}
+
+    @classmethod
+    def _load(cls):
+        if cls._solver is None:
+            import torch  # noqa: F401  (loads libcusolver.so.11; dlopen by soname then returns that copy)
+            lib = C.CDLL("libcusolver.so.11")
+            lib.cusolverDnCreate.argtypes = [C.POINTER(C.c_void_p)]
+            lib.cusolverDnSetStream.argtypes = [C.c_void_p, C.c_void_p]
+            lib.cusolverDnZheevd_bufferSize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                        C.POINTER(C.c_int)]
+            lib.cusolverDnZheevd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p]
+            for f in (lib.cusolverDnCreate, lib.cusolverDnSetStream, lib.cusolverDnZheevd_bufferSize, lib.cusolverDnZheevd):
+                f.restype = C.c_int
+            cls._solver = lib
+        return cls._solver
+
+    @classmethod
+    def eigh(cls, gram):
+        """gram: Hermitian complex128 CUDA matrix (n, n).  Returns (lam ascending (n,), vec (n, n) with eigenvectors in
+        its columns, info (int32 device tensor, 0 = converged)).  Enqueues on torch's current stream, never synchronises."""
+        import torch
+        lib = cls._load()
+        n = gram.shape[0]
+        dev = gram.device
+        key = (dev.index if dev.index is not None else torch.cuda.current_device())
+        handle = cls._handles.get(key)
+        if handle is None:
+            handle = C.c_void_p()
+            rc = lib.cusolverDnCreate(C.byref(handle))
+            if rc != 0:
+                raise _lib.QcaError(_lib.QCA_ERR_CUDA, f"cusolverDnCreate failed ({rc})")
+            cls._handles[key] = handle
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.cusolverDnSetStream(handle, C.c_void_p(stream))
+        # row-major Hermitian G is column-major conj(G): its eigenvectors are conj(v), written over the input in
+        # column-major order, i.e. the ROWS of the row-major tensor -> vec = a^H
+        a = _plain(gram).clone()
+        lam = torch.empty(n, dtype=torch.float64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        lwork = C.c_int()
+        rc = lib.cusolverDnZheevd_bufferSize(handle, 1, 0, n, C.c_void_p(a.data_ptr()), n, C.c_void_p(lam.data_ptr()), C.byref(lwork))
+        if rc != 0:
+            raise _lib.QcaError(_lib.QCA_ERR_CUDA, f"cusolverDnZheevd_bufferSize failed ({rc})")
+        work = cls._work.get(key)
+        if work is None or work.numel() < lwork.value:
+            work = torch.empty(max(lwork.value, 1), dtype=torch.complex128, device=dev)
+            cls._work[key] = work
+        rc = lib.cusolverDnZheevd(handle, 1, 0, n, C.c_void_p(a.data_ptr()), n, C.c_void_p(lam.data_ptr()),
+                                  C.c_void_p(work.data_ptr()), lwork.value, C.c_void_p(info.data_ptr()))
+        if rc != 0:
+            raise _lib.QcaError(_lib.QCA_ERR_CUDA, f"cusolverDnZheevd failed ({rc})")
+        return lam, a.conj().T, info
+
+
+def gram_svd_at_cap(mat, need: int, tail_floor: float, level_ratio: float = 1e-3):
+    """The `decided` branch of ``gram_svd`` (one Gram level, exactly `need` singular triplets kept because everything
+    beyond them still weighs >= tail_floor) computed SPECULATIVELY, without any host synchronisation: returns
+    (u, s, vh, ok) with `ok` a device bool that is true iff ``gram_svd`` would have taken that branch and returned these
+    numbers.  The caller checks `ok` later (one read per time step) and repeats the step with ``gram_svd`` if it is false."""
+    import torch
+    m, n = mat.shape
+    if m < n:
+        u, s, vh, ok = gram_svd_at_cap(mat.conj().T, need, tail_floor, level_ratio)
+        return vh.conj().T, s, u.conj().T, ok
+    gram = mat.conj().T @ mat
+    gram = 0.5 * (gram + gram.conj().T)
+    lam, vec, info = _CusolverEigh.eigh(gram)
+    lam, vec = lam.flip(0).clamp_min(0.0), vec.flip(1)
+    sig = torch.sqrt(lam)
+    accepted = (sig >= level_ratio * sig[0]).sum()
+    tail2 = lam[need:].sum()
+    floor = torch.clamp_min(1e-6 * sig[0], tail_floor)
+    ok = (info[0] == 0) & (accepted >= need) & (tail2 > 0) & (torch.sqrt(tail2) >= floor)
+    b = mat @ vec[:, :need]
+    s = torch.linalg.vector_norm(b, dim=0)
+    safe = torch.where(s > 0, s, torch.ones_like(s))
+    return b / safe, s, vec[:, :need].conj().T, ok
 
 
 _SM_COUNT = {}
@@ -148,7 +244,7 @@ def env_times_tensor(left, theta):
     """T[g, w, y, u] = sum_x left[x, w, y] * theta[g, x, u]   (first step of H_eff: L . theta)."""
     dx, w, dy = left.shape
     g, _, du = theta.shape
-    left, theta = left.contiguous(), theta.contiguous()
+    left, theta = _plain(left), _plain(theta)
     return zgemm_batched(left, theta, (g, w, dy, du), M=w * dy, N=du, K=dx, S=1, G=g,
                          a_strides=(0, 0, 1, w * dy), b_strides=(dx * du, 0, du))
 
@@ -157,7 +253,7 @@ def tensor_times_env(t, right):
     """out[g, y, v] = sum_{n,u} t[g, n, y, u] * right[u, n, v]   (last step of H_eff: T . R)."""
     g, w, dy, du = t.shape
     _, _, dv = right.shape
-    t, right = t.contiguous(), right.contiguous()
+    t, right = _plain(t), _plain(right)
     return zgemm_batched(t, right, (g, dy, dv), M=dy, N=dv, K=du, S=w, G=g,
                          a_strides=(w * dy * du, dy * du, du, 1), b_strides=(0, dv, w * dv))
 
@@ -243,7 +339,7 @@ def _heff_struct(left, right, op: SiteOperator):
     dl, wl, dl2 = left.shape
     dr, wr, dr2 = right.shape
     assert dl == dl2 and dr == dr2 and wl == op.wl and wr == op.wr, (left.shape, right.shape, op.wl, op.wr)
-    left, right = left.contiguous(), right.contiguous()
+    left, right = _plain(left), _plain(right)
     h = _lib.HeffStruct(left.data_ptr(), right.data_ptr(), op.rowptr.data_ptr(), op.col.data_ptr(), op.val.data_ptr(),
                         dl, dr, wl, wr, op.g, int(op.use_masks), (C.c_uint32 * 4)(*op.col_mask),
                         (C.c_uint32 * 4)(*op.row_mask))
@@ -254,7 +350,7 @@ def heff_apply(left, right, op: SiteOperator, psi):
     """H_eff psi (psi: (g, dl, dr) or any shape with g*dl*dr elements); returns a tensor like psi."""
     import torch
     h, keep = _heff_struct(left, right, op)
-    psi_c = psi.contiguous()
+    psi_c = _plain(psi)
     assert psi_c.numel() == op.g * h.dl * h.dr
     nbytes = C.c_uint64()
     _lib.check(_lib.lib.qca_heff_workspace_bytes(C.byref(h), 0, C.byref(nbytes)))
@@ -276,7 +372,7 @@ def env_grow(prev, site, op: SiteOperator):
     dl, wl, dl2 = prev.shape
     g, dx, dr = site.shape
     assert g == 2 and op.g == 2 and dx == dl == dl2 and wl == op.wl, (prev.shape, site.shape, op.g, op.wl)
-    prev, site = prev.contiguous(), site.contiguous()
+    prev, site = _plain(prev), _plain(site)
     h = _lib.HeffStruct(prev.data_ptr(), prev.data_ptr(), op.rowptr.data_ptr(), op.col.data_ptr(), op.val.data_ptr(),
                         dl, dr, wl, op.wr, 2, int(op.use_masks), (C.c_uint32 * 4)(*op.col_mask), (C.c_uint32 * 4)(*op.row_mask))
     nbytes = C.c_uint64()
@@ -294,7 +390,7 @@ def heff_expm(left, right, op: SiteOperator, psi, krylov_dim: int, t: float, spe
     spectral_bound: a bound of ||H_eff|| if known (the small exponential then is a Chebyshev series)."""
     import torch
     h, keep = _heff_struct(left, right, op)
-    psi_c = psi.contiguous()
+    psi_c = _plain(psi)
     assert psi_c.numel() == op.g * h.dl * h.dr
     nbytes = C.c_uint64()
     _lib.check(_lib.lib.qca_heff_workspace_bytes(C.byref(h), int(krylov_dim), C.byref(nbytes)))

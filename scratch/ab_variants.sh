@@ -1,7 +1,9 @@
 #!/bin/bash
 # A/B timing of library builds (scratch/variants/*.so) on ONE box: bench exact leg only, two rounds interleaved.
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_exact_gpu.py -m gpu -x -q 2>&1 | tail -3
+for v in "$@"; do
+  echo "== tests/test_exact_gpu.py with $v"; QCA_B200_LIBRARY=$PWD/scratch/variants/libqca_$v.so timeout 400 python -m pytest tests/test_exact_gpu.py -m gpu -x -q 2>&1 | tail -3
+done
 for round in 1 2; do
 for v in "$@"; do
   QCA_B200_LIBRARY=$PWD/scratch/variants/libqca_$v.so timeout 200 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-matched --no-tdvp \
@@ -19,5 +21,6 @@ PY
 done
 done
 # TDVP: parity tests and the chi = 256 step breakdown with the in-tree build
-timeout 600 python -m pytest tests/test_tdvp_gpu.py -m gpu -x -q 2>&1 | tail -4
-timeout 200 python scratch/tdvp_prof2.py > gpurun_out/r2c_tdvp_prof.txt 2>&1; head -12 gpurun_out/r2c_tdvp_prof.txt; tail -1 gpurun_out/r2c_tdvp_prof.txt
+timeout 600 python -m pytest tests/test_tdvp_gpu.py -m gpu -q 2>&1 | tail -8
+timeout 200 python scratch/tdvp_prof2.py > gpurun_out/r2e_tdvp_prof.txt 2>&1; head -14 gpurun_out/r2e_tdvp_prof.txt; tail -1 gpurun_out/r2e_tdvp_prof.txt
+QCA_TDVP_SYNC_SPLIT=1 timeout 200 python scratch/tdvp_prof2.py 2>&1 | head -1

@@ -128,6 +128,69 @@ def test_tdvp_agrees_with_exact_when_bond_cap_is_not_binding():
     assert overlap > 1 - 1e-5
 
 
+def _random_mps_at_cap(n, chi, seed=0):
+    rng = np.random.default_rng(seed)
+    dims = [min(2 ** i, 2 ** (n - i), chi) for i in range(n + 1)]
+    return qca_b200.MPS([(rng.standard_normal((2, dims[i], dims[i + 1])) + 1j * rng.standard_normal((2, dims[i], dims[i + 1])))
+                         / np.sqrt(2 * dims[i]) for i in range(n)])
+
+
+def _run_at_cap(n, chi, steps, monkeypatch, sync, break_flags=False):
+    import torch
+    import qca_b200.algorithms.tdvp as T
+    if sync:
+        monkeypatch.setenv("QCA_TDVP_SYNC_SPLIT", "1")
+    else:
+        monkeypatch.delenv("QCA_TDVP_SYNC_SPLIT", raising=False)
+    if break_flags:   # every speculation reports failure: each such step must be repeated with the synchronising split
+        real = T.gram_svd_at_cap
+        def broken(*a, **k):
+            u, s, vh, ok = real(*a, **k)
+            return u * 0.5, s, vh, torch.zeros_like(ok)
+        monkeypatch.setattr(T, "gram_svd_at_cap", broken)
+    rules = qca_b200.Rules(n, range(1, 2), 1)
+    args = qca_b200.Args(rules=rules, step_size=0.01, algorithm="2tdvp", max_bond_dim=chi, svd_epsilon=1e-12)
+    algo = qca_b200.TDVP(_random_mps_at_cap(n, chi), qca_b200.MPO.hamiltonian_from_rules(rules), args)
+    pops = []
+    for _ in range(steps):
+        algo.do_time_step()
+        pop, dpop, ent, bond = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n + 1)
+        algo.measure(pop, dpop, ent, bond)
+        pops.append(np.concatenate([pop, ent, bond]))
+    return np.array(pops), algo
+
+
+def test_speculative_split_equals_synchronising_split(monkeypatch):
+    """2tdvp at the bond cap: from the second step on the splits run without a host read (gram_svd_at_cap, cuSOLVER zheevd
+    called directly, flags checked once per step).  Same populations, entropies and bond dimensions as the synchronising
+    path (gram_svd); a speculation that reports failure makes the step repeat on the synchronising path."""
+    want, ref = _run_at_cap(12, 8, 4, monkeypatch, sync=True)
+    assert ref.speculative_splits == 0
+    got, algo = _run_at_cap(12, 8, 4, monkeypatch, sync=False)
+    assert algo.speculative_splits > 0 and algo.repeated_steps == 0
+    assert np.abs(got - want).max() < 1e-10
+    got, algo = _run_at_cap(12, 8, 4, monkeypatch, sync=False, break_flags=True)
+    assert algo.speculative_splits > 0 and algo.repeated_steps >= 1
+    assert np.abs(got - want).max() < 1e-10
+
+
+def test_direct_eigh_matches_torch():
+    """linalg._CusolverEigh (zheevd through ctypes, no host synchronisation) against torch.linalg.eigh."""
+    import torch
+    from qca_b200.linalg import _CusolverEigh
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for n in (1, 2, 7, 64, 200):
+        a = torch.randn(n, n, dtype=torch.complex128, device="cuda", generator=gen)
+        g = a.conj().T @ a
+        g = 0.5 * (g + g.conj().T)
+        lam, vec, info = _CusolverEigh.eigh(g)
+        assert int(info[0]) == 0
+        want = torch.linalg.eigvalsh(g)
+        assert (lam - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+        assert (g @ vec - vec * lam).abs().max().item() < 1e-11 * max(1.0, want.abs().max().item())
+        assert (vec.conj().T @ vec - torch.eye(n, dtype=g.dtype, device="cuda")).abs().max().item() < 1e-12
+
+
 def test_tdvp_rejects_unsupported_algorithm():
     rules = qca_b200.Rules(6, range(1, 2), 1)
     with pytest.raises(NotImplementedError):
@@ -255,6 +318,12 @@ def test_native_environment_update_matches_einsum(dl, dr, distance):
     want = torch.einsum("bmyr,bys->rms", t, a.conj())
     got = env_grow(prev, a, SiteOperator(w1, device="cuda"))
     assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
+    # a lazily conjugated tensor (torch only sets a flag; .contiguous() keeps it) must reach the library materialised:
+    # 2tdvp's right tensors come out of the split as such views
+    lazy = a.conj().resolve_conj().conj()
+    assert lazy.is_conj() and torch.equal(lazy, a)
+    got = env_grow(prev, lazy, SiteOperator(w1, device="cuda"))
     assert (got - want).abs().max().item() < 1e-12 * max(1.0, want.abs().max().item())
     # right: prev[u,w,v] with w the RIGHT bond of W, a[a,l,u]
     prev, a = rnd(dl, wr, dl), rnd(2, dr, dl)
