@@ -232,6 +232,7 @@ struct Engine {
     unsigned long long namps = 0;
     ShardMap shard{};     // local index -> global basis-state index
     double* plane[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    double* spare_plane = nullptr;   // the upload plane of a state that turned out real: kept for the next upload (see park_plane)
     int cur = 0;          // vector index of the resident state
     int nplanes = 0;      // 0: no state yet
     bool resolved = true; // sharded: planes agreed with the other ranks
@@ -293,6 +294,11 @@ static void invalidate_graphs(Engine* e) {
 static int32_t ensure_plane(Engine* e, int v, int p) {
     if (e->plane[v][p]) return QCA_OK;
     invalidate_graphs(e);
+    if (e->spare_plane) {   // (already counted in device_bytes)
+        e->plane[v][p] = e->spare_plane;
+        e->spare_plane = nullptr;
+        return QCA_OK;
+    }
     cudaError_t err = cudaMalloc(&e->plane[v][p], e->plane_bytes());
     if (err != cudaSuccess) {
         cudaGetLastError();
@@ -309,6 +315,18 @@ static void release_plane(Engine* e, int v, int p) {
     cudaFree(e->plane[v][p]);
     e->plane[v][p] = nullptr;
     e->st.device_bytes -= (double)e->plane_bytes();
+}
+
+// Take a plane out of use WITHOUT freeing it: every upload needs a second plane until the state is known to be real
+// in the rotated frame, and cudaFree / cudaMalloc of 8 GiB per upload synchronise the whole device -- in the
+// pipelined end-to-end path (two engines taking turns) an upload waited ~0.5 s for the OTHER engine's step to finish
+// (torch.profiler timeline, round 2).  One plane is parked per engine; a second one is freed.
+static void park_plane(Engine* e, int v, int p) {
+    if (!e->plane[v][p] || e->world > 1) return;
+    if (e->spare_plane) { release_plane(e, v, p); return; }
+    invalidate_graphs(e);
+    e->spare_plane = e->plane[v][p];
+    e->plane[v][p] = nullptr;
 }
 
 // entry[w] = activity of the middle K bits of the (K + 2d)-bit window w
@@ -774,7 +792,7 @@ static int32_t settle_planes(Engine* e, bool has_re, bool has_im) {
     } else {
         e->nplanes = 1;
     }
-    if (e->nplanes == 1) release_plane(e, e->cur, 1);
+    if (e->nplanes == 1) park_plane(e, e->cur, 1);
     e->resolved = true;
     return QCA_OK;
 }
@@ -1200,6 +1218,7 @@ int32_t qca_exact_destroy(qca_exact_t h) {
         }
     }
     for (int v = 0; v < 3; ++v) for (int p = 0; p < 2; ++p) if (e->plane[v][p]) cudaFree(e->plane[v][p]);
+    if (e->spare_plane) cudaFree(e->spare_plane);
     for (auto* p : e->d_tab_lo) if (p) cudaFree(p);
     for (auto* p : e->d_tab_hi) if (p) cudaFree(p);
     for (auto& tb : e->tabs3) { if (tb.thr) cudaFree(tb.thr); if (tb.row) cudaFree(tb.row); }
