@@ -190,6 +190,13 @@ static __device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
+// true in exactly one lane of the (converged) warp; tells the compiler so (no per-lane serialisation of the
+// uniform-datapath instructions in the branch it guards)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 // global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -208,12 +215,28 @@ __device__ __forceinline__ void stage_tile_bulk(double* tile, const double* in, 
     constexpr int NPIECES = 1 << (TILE_BITS - PIECE_BITS);
     constexpr unsigned low_mask = (1u << L) - 1u;
     if (tid == 0) mbar_arrive_expect_tx(bar, 8u << TILE_BITS);
+#ifndef QCA_THREAD_ISSUE
+    // one elected lane per warp issues the warp's share in a warp-uniform loop (see pass_kernel_v3)
+    constexpr int WARPS = THREADS / 32;
+    constexpr int PER_WARP = NPIECES >= WARPS ? NPIECES / WARPS : 1;
+    const unsigned wu = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if ((NPIECES >= WARPS || wu < (unsigned)NPIECES) && elect_one()) {
+#pragma unroll 4
+        for (int i = 0; i < PER_WARP; ++i) {
+            const unsigned y = (wu * PER_WARP + (unsigned)i) << PIECE_BITS;
+            const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+            bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, bar);
+        }
+    }
+    __syncwarp();
+#else
 #pragma unroll 1
     for (int r = (int)tid; r < NPIECES; r += THREADS) {
         const unsigned y = (unsigned)r << PIECE_BITS;   // tile-local index of the first amplitude of the piece
         const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
         bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, bar);
     }
+#endif
     mbar_wait(bar, parity);
 }
 

@@ -31,6 +31,13 @@ constexpr int kRowShift3 = kTile3 - kRegHigh;    // 10: tile bits 10..13 are reg
 constexpr int kThrBits3 = kRowShift3 - 1;        // 9 thread bits (tile bits 1..9)
 constexpr int kMaxClusterBits = 3;               // portable cluster size 8
 constexpr int kRing3Rows = 12;                   // 8 KiB each
+// Request order and ring depth (A/B switches; the defaults are the measured winners, see the staging block of the kernel):
+#ifndef QCA_V3_RING_FIRST
+#define QCA_V3_RING_FIRST 0   // operand ring requested before the tile: 0 never (default), 1 in pass 0 only, 2 always (round-2 start)
+#endif
+#ifndef QCA_V3_DU1
+#define QCA_V3_DU1 12  // ring rows in flight when a launch streams ONE operand (later passes); <= kRing3Rows
+#endif
 constexpr int kPass3TileRingBytes = (8 << kTile3) + kRing3Rows * kPass3Threads * 16;   // 224 KiB
 constexpr int kPass3SmemBytes = kPass3TileRingBytes + 16;   // + the mbarrier of the bulk-copied tile
 
@@ -85,7 +92,7 @@ template <typename I, int L, bool FLIP_LOW, int NUNC, int CB>
 __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Args a) {
     constexpr int M = kTile3 - L;
     constexpr int QLO = FLIP_LOW ? 0 : L;
-    constexpr int DU = NUNC == 0 ? 0 : (NUNC == 1 ? 8 : 6);
+    constexpr int DU = NUNC == 0 ? 0 : (NUNC == 1 ? QCA_V3_DU1 : 6);
     static_assert(NUNC * DU <= kRing3Rows, "ring budget");
     static_assert(FLIP_LOW ? (M == 0) : (M >= 1), "geometry");
     static_assert(L >= 4 && CB >= 0 && CB <= kMaxClusterBits, "geometry");
@@ -119,13 +126,21 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
 #pragma unroll
         for (int k = 0; k < NUNC; ++k) cp_async16(local_slot(k, e), a.opnd[k][plane] + row_x(e));
     };
-    if (NUNC) {
+    auto ring_prologue = [&]() {
+        if (NUNC) {
 #pragma unroll
-        for (int e = 0; e < DU; ++e) {
-            local_fetch(e);
-            cp_async_commit();
+            for (int e = 0; e < DU; ++e) {
+                local_fetch(e);
+                cp_async_commit();
+            }
         }
-    }
+    };
+#if defined(QCA_THREAD_ISSUE) || defined(QCA_V3_LDG_TILE)
+    constexpr bool RING_FIRST = true;
+#else
+    constexpr bool RING_FIRST = (QCA_V3_RING_FIRST == 2) || (QCA_V3_RING_FIRST == 1 && FLIP_LOW);
+#endif
+    if (RING_FIRST) ring_prologue();
     // ---- stage the tile --------------------------------------------------------------------------------
     double2 v[kRows];
 #ifndef QCA_V3_LDG_TILE
@@ -146,12 +161,42 @@ __global__ void __launch_bounds__(kPass3Threads, 1) pass_kernel_v3(const Pass3Ar
         if (tid == 0) mbar_arrive_expect_tx(tile_bar, 8u << kTile3);
         constexpr int PIECE_BITS = L < 10 ? L : 10;
         constexpr int NPIECES = 1 << (kTile3 - PIECE_BITS);
+#ifndef QCA_THREAD_ISSUE
+        // THE TILE IS REQUESTED BEFORE THE OPERAND RING, by one elected lane per warp in a warp-uniform loop.
+        // A CTA cannot compute before its tile has landed but needs only the first ring row at the end of its first
+        // row, and one CTA per SM means nothing else runs while it waits: with the ring's 64-96 KiB queued ahead of
+        // the tile (round-2 start) ncu put 34 % of all warp samples of a later pass behind the tile's mbarrier, plus
+        // 11 % into the ELECT / R2UR / BRA.U.ANY loop in which the compiler serialises the (uniform-datapath) UBLKCP
+        // of the 32 lanes of a warp when every thread issues one piece.  Same-box interleaved A/B at N = 30
+        // (profiles/r02_ab_staging_order.txt): later passes 4.68 / 4.74 -> 4.09 / 4.14 ms (6.3 TB/s, 0.96 of the
+        // measured copy peak), 0.954 -> 1.021 steps/s; the issue scheme alone, with the ring still first, gains
+        // nothing (4.91 / 5.02 ms), the order is what pays; a 12-row ring is worth +0.4 % once the tile goes first and
+        // costs 5 % when it does not.  Pass 0 slows by the clock the power cap takes back (5.17 -> 5.41 ms at
+        // 1777 -> 1695 MHz): with every pass at the DRAM roofline the step is power-limited.
+        {
+            constexpr int PER_WARP = NPIECES / (kPass3Threads / 32);
+            static_assert(PER_WARP >= 1, "at least one piece per warp");
+            const unsigned wu = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, known to be warp-uniform
+            if (elect_one()) {
+#pragma unroll 4
+                for (int i = 0; i < PER_WARP; ++i) {
+                    const unsigned r = wu * PER_WARP + (unsigned)i;
+                    const unsigned y = r << PIECE_BITS;
+                    const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
+                    bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, tile_bar);
+                }
+            }
+            __syncwarp();
+        }
+        if (!RING_FIRST) ring_prologue();
+#else
 #pragma unroll 1
         for (int r = (int)tid; r < NPIECES; r += kPass3Threads) {
             const unsigned y = (unsigned)r << PIECE_BITS;   // tile-local index of the first amplitude of the piece
             const I x = base | (I)(y & low_mask) | ((I)(y >> L) << H0);
             bulk_g2s(smem_u32(tile + y), in + x, 8u << PIECE_BITS, tile_bar);
         }
+#endif
         mbar_wait(tile_bar, 0);
 #pragma unroll
         for (int e = 0; e < kRows; ++e) v[e] = tile2[(e << kThrBits3) | tid];

@@ -1,0 +1,34 @@
+#!/bin/bash
+# A/B of tile-staging variants of the pass kernels (scratch/variants/*.so, built with -DQCA_V3_WARP_ISSUE / -DQCA_V3_DU1=12)
+# against the in-tree build on ONE box: parity tests first, then the exact leg of bench.py, two rounds interleaved.
+mkdir -p gpurun_out
+T0=$(date +%s)
+for v in wi_du12 wi; do
+  echo "== tests/test_exact_gpu.py with $v"; QCA_B200_LIBRARY=$PWD/scratch/variants/libqca_$v.so timeout 300 python -m pytest tests/test_exact_gpu.py -m gpu -x -q 2>&1 | tail -2
+done
+echo "== subset with du12"; QCA_B200_LIBRARY=$PWD/scratch/variants/libqca_du12.so timeout 200 python -m pytest tests/test_exact_gpu.py -m gpu -x -q -k "fast_kernel or cluster or c_oracle_rows" 2>&1 | tail -2
+echo "tests done after $(( $(date +%s) - T0 )) s"
+one() {  # tag library env...
+  tag=$1; lib=$2; shift 2
+  env "$@" QCA_B200_LIBRARY=$lib timeout 150 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-matched --no-tdvp \
+      2> gpurun_out/r2i_$tag.err > gpurun_out/r2i_${tag}_$round.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r2i_${tag}_$round.json"))
+    r = d["roofline"]
+    print("$tag round $round: steps/s", round(d["value"], 4), "frac", round(r["frac"], 4), "ms by pass", [round(x, 3) for x in r["avg_launch_ms_by_pass"]],
+          "checksum", d["checksum"]["ok"], d["checksum"]["max_abs_diff_vs_committed"], "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+except Exception as e:
+    print("$tag FAILED", e)
+PY
+}
+for round in 1 2; do
+  one base $PWD/quantum-cellular-automaton_b200/libqca_b200.so QCA_X=1
+  one wi $PWD/scratch/variants/libqca_wi.so QCA_X=1
+  one wi_du12 $PWD/scratch/variants/libqca_wi_du12.so QCA_X=1
+  one du12 $PWD/scratch/variants/libqca_du12.so QCA_X=1
+  [ $round = 1 ] && one v2_kernels $PWD/scratch/variants/libqca_wi.so QCA_V2_KERNELS=1
+  [ $round = 1 ] && one v2_kernels_base $PWD/quantum-cellular-automaton_b200/libqca_b200.so QCA_V2_KERNELS=1
+done
+echo "all done after $(( $(date +%s) - T0 )) s"
