@@ -1,5 +1,5 @@
 """Where does a chi=256 2TDVP step spend its time?  GPU-busy time by kernel (torch.profiler) against
-wall time, plus phase timers.  usage: python scratch/tdvp_prof2.py [ncells] [chi]"""
+wall time, plus phase timers.  usage: python scratch/tdvp_prof2.py [ncells] [chi] [1tdvp|2tdvp]"""
 import sys, time, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +8,7 @@ from torch.profiler import profile, ProfilerActivity
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 chi = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+algorithm = sys.argv[3] if len(sys.argv) > 3 else "2tdvp"
 
 
 def random_mps(n, chi, seed=0):
@@ -17,9 +18,11 @@ def random_mps(n, chi, seed=0):
 
 
 rules = qca_b200.Rules(n, range(1, 2), 1)
-args = qca_b200.Args(rules=rules, step_size=0.005, algorithm="2tdvp", max_bond_dim=chi, svd_epsilon=1e-14)
+args = qca_b200.Args(rules=rules, step_size=0.005, algorithm=algorithm, max_bond_dim=chi, svd_epsilon=1e-14)
+t_init = time.time()
 algo = qca_b200.TDVP(random_mps(n, chi), qca_b200.MPO.hamiltonian_from_rules(rules), args)
 torch.cuda.synchronize()
+print(f"{algorithm}: constructor (canonicalisation + right environments) {time.time() - t_init:.2f} s")
 for _ in range(2):
     algo.do_time_step()
 torch.cuda.synchronize()
@@ -27,7 +30,7 @@ t0 = time.time()
 algo.do_time_step()
 torch.cuda.synchronize()
 wall = time.time() - t0
-print(f"N={n} chi={chi}: wall {wall:.3f} s/step, heff applications {algo.heff_applications // 3}")
+print(f"{algorithm} N={n} chi={chi}: wall {wall:.3f} s/step, heff applications {algo.heff_applications // 3}")
 
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     algo.do_time_step()

@@ -223,6 +223,27 @@ def test_householder_qr_is_numpy_qr(m, n, complete):
         assert np.abs(q - q_np).max() < 1e-11
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,complete", [(512, 256, False), (256, 512, False), (512, 256, True), (130, 67, False), (96, 96, True),
+                                           (1024, 32, False), (3, 200, False)])
+def test_grid_qr_equals_single_cta_qr(m, n, complete, monkeypatch):
+    """The cooperative multi-CTA Householder kernels against the one-CTA kernels they replace: same reflectors, same
+    order of operations per column -- equal to rounding of the column norms."""
+    import torch
+    from qca_b200.linalg import householder_qr
+    rng = np.random.default_rng(7 * m + n)
+    a = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    a[:, min(n - 1, 2)] = 0.0                       # a zero column: tau = 0
+    dev = torch.as_tensor(a, device="cuda")
+    q1, r1 = householder_qr(dev, complete=complete)
+    monkeypatch.setenv("QCA_QR_SINGLE_CTA", "1")
+    q0, r0 = householder_qr(dev, complete=complete)
+    assert q1.shape == q0.shape and r1.shape == r0.shape
+    assert float((r1 - r0).abs().max()) < 1e-12 * max(1.0, float(r0.abs().max()))
+    assert float((q1 - q0).abs().max()) < 1e-12
+    assert float((q1 @ r1 - dev).abs().max()) < 1e-11
+
+
 def test_gram_svd_on_device_matches_lapack():
     import torch
     from qca_b200.linalg import gram_svd
