@@ -303,6 +303,58 @@ __global__ void __launch_bounds__(kQrGridThreads) qr_form_cols_kernel(const cplx
     }
 }
 
+
+// The same, with the column in REGISTERS (m <= 32 * S): lane l owns the rows i = l + 32 s for the whole job, so nothing
+// goes through memory between two reflectors.  (qr_form_cols_kernel re-reads and re-writes its column in global memory
+// for every reflector, and the lane that owns a row changes with k: 0.81 ms at 512 x 256, two L2 round trips per reflector.)
+template <int S>
+__global__ void __launch_bounds__(kQrGridThreads) qr_form_cols_reg_kernel(const cplx* __restrict__ a, int m, int n,
+                                                                            const cplx* __restrict__ tau, cplx* __restrict__ q,
+                                                                            int kq, cplx* __restrict__ r) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kmax = m < n ? m : n;
+    const size_t gtid = (size_t)blockIdx.x * kQrGridThreads + tid, gsize = (size_t)gridDim.x * kQrGridThreads;
+    for (size_t idx = gtid; idx < (size_t)kq * n; idx += gsize) {
+        const int i = (int)(idx % kq), j = (int)(idx / kq);
+        r[idx] = (i <= j && i < kmax) ? a[(size_t)j * m + i] : cplx{0.0, 0.0};
+    }
+    const int gwarps = gridDim.x * kQrGridWarps;
+    for (int j = blockIdx.x * kQrGridWarps + warp; j < kq; j += gwarps) {
+        cplx c[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) c[s] = (lane + 32 * s == j) ? cplx{1.0, 0.0} : cplx{0.0, 0.0};
+        for (int k = (j < kmax - 1 ? j : kmax - 1); k >= 0; --k) {
+            const cplx t = tau[k];
+            if (t.x == 0.0 && t.y == 0.0) continue;
+            const cplx* vk = a + (size_t)k * m;
+            cplx vv[S];
+            cplx w = {0.0, 0.0};
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int i = lane + 32 * s;
+                vv[s] = (i > k && i < m) ? vk[i] : ((i == k) ? cplx{1.0, 0.0} : cplx{0.0, 0.0});   // rows above k: untouched
+                const cplx p = cmulc(vv[s], c[s]);
+                w.x += p.x; w.y += p.y;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
+                w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+            }
+            const cplx f = cmul(t, w);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const cplx p = cmul(vv[s], f);
+                c[s].x -= p.x; c[s].y -= p.y;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int i = lane + 32 * s;
+            if (i < m) q[(size_t)j * m + i] = c[s];
+        }
+    }
+}
+
 }  // namespace qca
 
 extern "C" {
@@ -333,8 +385,16 @@ int32_t qca_qr_householder(void* a, int32_t m, int32_t n, void* tau, void* q, in
         QCA_CUDA(cudaLaunchCooperativeKernel((const void*)qca::qr_factor_grid_kernel, dim3(grid), dim3(qca::kQrGridThreads), fargs, smem, s));
         int fgrid = (kq + qca::kQrGridWarps - 1) / qca::kQrGridWarps;
         if (fgrid > 4 * sms) fgrid = 4 * sms;
-        qca::qr_form_cols_kernel<<<fgrid, qca::kQrGridThreads, 0, s>>>((const qca::cplx*)a, m, n, (const qca::cplx*)tau,
-                                                                      (qca::cplx*)q, kq, (qca::cplx*)r);
+        const bool in_regs = getenv("QCA_QR_FORM_GLOBAL") == nullptr;
+        if (in_regs && m <= 128)
+            qca::qr_form_cols_reg_kernel<4><<<fgrid, qca::kQrGridThreads, 0, s>>>((const qca::cplx*)a, m, n, (const qca::cplx*)tau,
+                                                                                 (qca::cplx*)q, kq, (qca::cplx*)r);
+        else if (in_regs && m <= 512)
+            qca::qr_form_cols_reg_kernel<16><<<fgrid, qca::kQrGridThreads, 0, s>>>((const qca::cplx*)a, m, n, (const qca::cplx*)tau,
+                                                                                  (qca::cplx*)q, kq, (qca::cplx*)r);
+        else
+            qca::qr_form_cols_kernel<<<fgrid, qca::kQrGridThreads, 0, s>>>((const qca::cplx*)a, m, n, (const qca::cplx*)tau,
+                                                                          (qca::cplx*)q, kq, (qca::cplx*)r);
         QCA_CUDA(cudaGetLastError());
         return QCA_OK;
     }
