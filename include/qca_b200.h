@@ -223,6 +223,10 @@ int32_t qca_exact_reset_stats(qca_exact_t h);
  * All pointers are DEVICE pointers to column-major complex128.  a (m x n) is overwritten by the
  * factorisation; q receives m x kq (kq = min(m,n) "reduced" or m "complete"), r receives kq x n.
  * The reference's results depend on this sign convention (see csrc/qca_linalg.cu).
+ * The factorisation is a COOPERATIVE launch over up to one CTA per SM (one grid barrier per column): the device must
+ * support cooperative launches, the call must not sit inside a CUDA-graph capture, and it starts once its whole grid
+ * can be resident.  Environment (tests / A-B): QCA_QR_SINGLE_CTA = the one-CTA kernels of round 1,
+ * QCA_QR_FORM_GLOBAL = form Q with the column in global memory also for m <= 512.
  * ---------------------------------------------------------------------- */
 int32_t qca_qr_householder(void* a, int32_t m, int32_t n, void* tau, void* q, int32_t kq, void* r, void* stream);
 
