@@ -78,3 +78,70 @@ def test_gram_svd_reports_a_decided_truncation():
     assert not info.get("decided")
     tail = np.sqrt(np.cumsum((s.numpy() ** 2)[::-1])[::-1] + float(rest) ** 2)
     assert (tail < 1e-12).nonzero()[0][0] == 6
+
+
+# -- statement-level model of the multi-CTA Householder QR (csrc/qca_linalg.cu) ---------------------------------
+def _zlarfg(col, k):
+    """What every CTA of qr_factor_grid_kernel derives from column k: (tau, beta or None, reflector with v[k] = 1)."""
+    alpha = col[k]
+    xnorm2 = float(np.sum(np.abs(col[k + 1:]) ** 2))
+    v = col.copy()
+    v[:k] = 0.0
+    v[k] = 1.0
+    if xnorm2 == 0.0 and alpha.imag == 0.0:
+        return 0.0j, None, v                      # H = I: the column (and its diagonal) stay as they are
+    beta = -np.copysign(np.sqrt(alpha.real ** 2 + alpha.imag ** 2 + xnorm2), alpha.real)
+    tau = complex((beta - alpha.real) / beta, -alpha.imag / beta)
+    v[k + 1:] = col[k + 1:] / (alpha - beta)
+    return tau, beta, v
+
+
+def grid_qr_model(a, complete=False):
+    """qr_factor_grid_kernel (right-looking: one reflector, then every trailing column on its own) followed by
+    qr_form_cols_reg_kernel (column j of Q = H_0 ... H_min(j, kmax-1) e_j, every column on its own)."""
+    a = np.array(a, dtype=np.complex128)
+    m, n = a.shape
+    kmax = min(m, n)
+    taus, vs = [], []
+    for k in range(kmax):
+        tau, beta, v = _zlarfg(a[:, k], k)
+        if tau != 0:
+            for j in range(k + 1, n):             # one warp per column in the kernel
+                w = np.vdot(v[k:], a[k:, j])
+                a[k:, j] -= v[k:] * (np.conj(tau) * w)
+            a[k + 1:, k] = v[k + 1:]              # written by CTA 0 after the grid barrier
+            a[k, k] = beta
+        taus.append(tau)
+        vs.append(v)
+    kq = m if complete else kmax
+    q = np.zeros((m, kq), dtype=np.complex128)
+    for j in range(kq):                           # one warp per column, the column in registers
+        c = np.zeros(m, dtype=np.complex128)
+        c[j] = 1.0
+        for k in range(min(j, kmax - 1), -1, -1):
+            if taus[k] != 0:
+                c[k:] -= vs[k][k:] * (taus[k] * np.vdot(vs[k][k:], c[k:]))
+        q[:, j] = c
+    r = np.triu(a)[:kq, :]
+    return q, r
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 1), (4, 2), (2, 4), (16, 8), (8, 16), (33, 7), (64, 32), (40, 40)])
+@pytest.mark.parametrize("complete", [False, True])
+def test_grid_qr_model_is_numpy_qr(m, n, complete):
+    """The algorithm of the multi-CTA kernels reproduces numpy.linalg.qr including the signs of R's diagonal, the
+    tau = 0 branch of a zero column and the completion of Q."""
+    rng = np.random.default_rng(100 * m + n)
+    mat = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    cases = [mat]
+    if n > 1:
+        deficient = mat.copy(); deficient[:, 1] = 0.0
+        cases.append(deficient)
+    cases.append(np.eye(m, n, dtype=np.complex128))            # every reflector is the identity or a sign flip
+    for a in cases:
+        q_np, r_np = np.linalg.qr(a, mode="complete" if complete else "reduced")
+        q, r = grid_qr_model(a, complete)
+        assert q.shape == q_np.shape and r.shape == r_np.shape
+        assert np.abs(r - r_np).max() < 1e-12 * max(1.0, np.abs(r_np).max())
+        assert np.abs(q - q_np).max() < 1e-11
+        assert np.abs(q @ r - a).max() < 1e-12
